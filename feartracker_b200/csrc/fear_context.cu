@@ -1,0 +1,785 @@
+// libfear_b200.so -- executor + C ABI of the FEAR-XS hot path on B200 (sm_100a).
+// See include/fear_b200.h for the contract and DESIGN.md for the data layout.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fear_b200.h"
+#include "arch.h"
+#include "kernels_ffma.cuh"
+#include "kernels_tc.cuh"
+
+using namespace fear;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return set_err((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define FEAR_TRY(expr)       \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+// ------------------------------------------------------------------------------ stages
+enum Stage {
+  ST_STEM = 0,
+  ST_BACKBONE_PW,
+  ST_BACKBONE_DW,
+  ST_NECK,
+  ST_HEAD_DW,
+  ST_HEAD_PW,
+  ST_CORR,
+  ST_PRED,
+  ST_DECODE,
+  ST_LAYOUT,
+  ST_COUNT
+};
+static const char* kStageNames[ST_COUNT] = {"stem",    "backbone_pw", "backbone_dw", "neck",   "head_dw",
+                                            "head_pw", "corr",        "pred",        "decode", "layout"};
+
+enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };
+
+struct Options {
+  int corr = IMPL_FFMA;
+  int pw = IMPL_FFMA;
+};
+static Options g_default_options;
+
+struct PwW {
+  const float* w = nullptr;  // [cout][cin]
+  const float* b = nullptr;
+  int cin = 0, cout = 0;
+};
+struct DwW {
+  const float* w = nullptr;  // [k*k][c]
+  const float* b = nullptr;
+  int c = 0, k = 0;
+};
+struct BlockW {
+  PwW pw, pwl;
+  DwW dw;
+};
+struct BranchW {
+  DwW enc_dw, corr_dw;
+  PwW enc_pw, corr_pw;
+};
+struct TowerW {
+  DwW dw[2];
+  PwW pw[2];
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int stage;
+};
+
+struct FearContext {
+  int device = 0;
+  Options opt;
+  float* d_weights = nullptr;
+  const float *stem_w = nullptr, *stem_b = nullptr;
+  BlockW blocks[kNumBlocks];
+  PwW neck;
+  BranchW branch[2];  // 0 = cls, 1 = reg
+  TowerW tower[2];    // 0 = bbox, 1 = cls
+  DwW pred_dw[2];     // 0 = bbox, 1 = cls
+  const float *pred_w[2] = {nullptr, nullptr}, *pred_b[2] = {nullptr, nullptr};
+
+  int reserved = 0;
+  float* ws = nullptr;
+  // backbone ping-pong (per frame sizes in floats)
+  float *bufX = nullptr, *bufY = nullptr, *bufE = nullptr, *bufD = nullptr;
+  // head
+  float *hF = nullptr, *hT = nullptr, *hCAT[2] = {nullptr, nullptr}, *hD[2] = {nullptr, nullptr}, *hP = nullptr;
+  float* hQ[2] = {nullptr, nullptr};  // tower outputs: [0] = bbox tower (x_reg), [1] = cls tower
+  float *zt = nullptr, *mapB = nullptr, *mapC = nullptr;
+
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<EventPair> events;
+  size_t events_used = 0;
+  double stage_ms[ST_COUNT] = {0};
+  int64_t stage_launches[ST_COUNT] = {0};
+};
+
+static constexpr int64_t kActX = 128 * 128 * 16;  // largest block input / output per frame (floats)
+static constexpr int64_t kActE = 128 * 128 * 96;  // largest expanded tensor (xif2_0.pw)
+static constexpr int64_t kActD = 64 * 64 * 96;    // largest depthwise output (xif2_0.dw)
+
+// RAII bracket around one kernel launch: counts it and, when profiling, records events.
+struct LaunchScope {
+  FearContext* c;
+  cudaStream_t s;
+  EventPair* ev = nullptr;
+  LaunchScope(FearContext* c_, int stage, cudaStream_t s_) : c(c_), s(s_) {
+    if (!c) return;
+    c->launches++;
+    c->stage_launches[stage]++;
+    if (c->profiling && c->events_used < c->events.size()) {
+      ev = &c->events[c->events_used++];
+      ev->stage = stage;
+      cudaEventRecord(ev->a, s);
+    }
+  }
+  ~LaunchScope() {
+    if (ev) cudaEventRecord(ev->b, s);
+  }
+};
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ launchers
+static int launch_gemm_ffma(FearContext* c, int stage, cudaStream_t s, const float* A, int lda, long long sA,
+                            const float* Bw, int ldb, long long sB, const float* bias, const float* R, int ldr,
+                            float* C, int ldc, long long sC, int M, int N, int K, int relu, int batch) {
+  LaunchScope scope(c, stage, s);
+#define GEMM_CASE(TN_)                                                                                    \
+  {                                                                                                       \
+    dim3 grid((M + 127) / 128, (N + 8 * TN_ - 1) / (8 * TN_), batch);                                     \
+    gemm_nt_ffma_kernel<TN_><<<grid, 256, 0, s>>>(A, lda, sA, Bw, ldb, sB, bias, R, ldr, C, ldc, sC, M, N, K, \
+                                                  relu);                                                  \
+  }
+  if (N % 64 == 0) GEMM_CASE(8)
+  else if (N % 56 == 0) GEMM_CASE(7)
+  else if (N % 48 == 0) GEMM_CASE(6)
+  else if (N % 32 == 0) GEMM_CASE(4)
+  else if (N % 24 == 0) GEMM_CASE(3)
+  else GEMM_CASE(2)
+#undef GEMM_CASE
+  return check_launch("gemm_nt_ffma_kernel");
+}
+
+// 1x1 conv over M pixels: out = act(A * W^T + b (+R)).
+static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, int lda, const PwW& w, const float* R,
+                     int ldr, float* C, int ldc, int M, int relu) {
+  if (c->opt.pw == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
+    LaunchScope scope(c, stage, s);
+    int r = tc::launch_pw(s, A, lda, w.w, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
+    if (r) return set_err(r, "tcgen05 pw launch failed (%d)", r);
+    return check_launch("tc::pw");
+  }
+  return launch_gemm_ffma(c, stage, s, A, lda, 0, w.w, w.cin, 0, w.b, R, ldr, C, ldc, 0, M, w.cout, w.cin, relu, 1);
+}
+
+static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in, const DwW& w, float* out, int B, int H,
+                     int W, int stride, bool relu) {
+  LaunchScope scope(c, stage, s);
+  const int C4 = w.c / 4;
+  const long long total = (long long)B * (H / stride) * (W / stride) * C4;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  const float4* i4 = reinterpret_cast<const float4*>(in);
+  const float4* w4 = reinterpret_cast<const float4*>(w.w);
+  const float4* b4 = reinterpret_cast<const float4*>(w.b);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  const bool bias = w.b != nullptr;
+  if (w.k == 3 && stride == 1 && relu && bias)
+    dw_conv_nhwc_kernel<3, 1, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+  else if (w.k == 3 && stride == 2 && relu && bias)
+    dw_conv_nhwc_kernel<3, 2, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+  else if (w.k == 5 && stride == 1 && relu && bias)
+    dw_conv_nhwc_kernel<5, 1, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+  else if (w.k == 5 && stride == 2 && relu && bias)
+    dw_conv_nhwc_kernel<5, 2, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+  else if (w.k == 3 && stride == 1 && !relu && !bias)
+    dw_conv_nhwc_kernel<3, 1, false, false><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+  else
+    return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
+                   (int)bias);
+  return check_launch("dw_conv_nhwc_kernel");
+}
+
+static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int ldin, long long sIn, float* out,
+                            int ldout, long long sOut, int R, int Cn, int batch) {
+  LaunchScope scope(c, ST_LAYOUT, s);
+  dim3 grid((Cn + 31) / 32, (R + 31) / 32, batch);
+  transpose_kernel<<<grid, 256, 0, s>>>(in, ldin, sIn, out, ldout, sOut, R, Cn);
+  return check_launch("transpose_kernel");
+}
+
+// cat[b, p, 256 + k] = sum_c zt[b, k, c] * cat[b, p, c]    (MobileCorrelation matmul, blocks.py:123)
+static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B) {
+  if (opt.corr == IMPL_TC) {
+    LaunchScope scope(c, ST_CORR, s);
+    int r = tc::launch_corr(s, zt, Bz, cat, B);
+    if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
+    return check_launch("tc::corr");
+  }
+  return launch_gemm_ffma(c, ST_CORR, s, cat, kCatC, (long long)kScorePix * kCatC, zt, kFeatC,
+                          Bz == 1 ? 0 : (long long)kCorrC * kFeatC, nullptr, nullptr, 0, cat + kFeatC, kCatC,
+                          (long long)kScorePix * kCatC, kScorePix, kCorrC, kFeatC, 0, B);
+}
+
+// ------------------------------------------------------------------------------ executor
+// img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer)
+static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, const float** feat) {
+  {
+    LaunchScope scope(c, ST_STEM, s);
+    const long long total = (long long)B * (H / 2) * (W / 2);
+    stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(img, c->stem_w, c->stem_b, c->bufX, B, H, W);
+    FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
+  }
+  int h = H / 2, w = W / 2;
+  float *X = c->bufX, *Y = c->bufY;
+  for (int i = 0; i < kNumBlocks; ++i) {
+    const IrfSpec& sp = kBlocks[i];
+    const BlockW& bw = c->blocks[i];
+    const int M = B * h * w;
+    const float* E = X;
+    if (sp.has_pw()) {
+      FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
+      E = c->bufE;
+    }
+    FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
+    h /= sp.stride;
+    w /= sp.stride;
+    const int Mo = B * h * w;
+    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, Y,
+                       sp.cout, Mo, 0));
+    float* t = X;
+    X = Y;
+    Y = t;
+  }
+  *feat = X;
+  return 0;
+}
+
+// img (B,3,H,W) NCHW -> out NHWC [B][H/16 * W/16][256]   (FEARNet.get_features, fear_net.py:63-66)
+static int run_features(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, float* out) {
+  const float* X = nullptr;
+  FEAR_TRY(run_backbone(c, s, img, B, H, W, &X));
+  return launch_pw(c, ST_NECK, s, X, kBackboneC, c->neck, nullptr, 0, out, kFeatC, B * (H / 16) * (W / 16), 0);
+}
+
+// F: NHWC search features [B][256][256]; zt: [Bz][64][256]; outputs NCHW maps.
+static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, const float* F, int B, float* bbox,
+                    float* cls) {
+  const int M = B * kScorePix;
+  for (int br = 0; br < 2; ++br) {
+    const BranchW& w = c->branch[br];
+    // MatrixMobile: x -> dw3x3 -> 1x1 (+BN) -> ReLU, written into channels [0,256) of the concat buffer
+    FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, F, w.enc_dw, c->hT, B, kScore, kScore, 1, false));
+    FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, w.enc_pw, nullptr, 0, c->hCAT[br], kCatC, M, 1));
+    // pixel-wise correlation into channels [256,320)
+    FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[br], B));
+    // MobileCorrelation.enc: dw3x3(320) -> 1x1 320->256 (+BN) -> ReLU
+    FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, c->hCAT[br], w.corr_dw, c->hT, B, kScore, kScore, 1, false));
+    FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kCatC, w.corr_pw, nullptr, 0, c->hD[br], kFeatC, M, 1));
+  }
+  // towers: tower[0] = bbox_tower on reg branch (hD[1]); tower[1] = cls_tower on cls branch (hD[0])
+  for (int t = 0; t < 2; ++t) {
+    const float* x = c->hD[t == 0 ? 1 : 0];
+    float* outs[2] = {c->hP, c->hQ[t]};
+    for (int i = 0; i < 2; ++i) {
+      FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, x, c->tower[t].dw[i], c->hT, B, kScore, kScore, 1, false));
+      FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, c->tower[t].pw[i], nullptr, 0, outs[i], kFeatC, M, 1));
+      x = outs[i];
+    }
+    FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, x, c->pred_dw[t], c->hT, B, kScore, kScore, 1, false));
+    LaunchScope scope(c, ST_PRED, s);
+    const unsigned blocks = (unsigned)((M * 32 + 255) / 256);
+    if (t == 0)
+      pred_pw_kernel<4, true><<<blocks, 256, 0, s>>>(c->hT, c->pred_w[0], c->pred_b[0], bbox, B);
+    else
+      pred_pw_kernel<1, false><<<blocks, 256, 0, s>>>(c->hT, c->pred_w[1], c->pred_b[1], cls, B);
+    FEAR_TRY(check_launch("pred_pw_kernel"));
+  }
+  return 0;
+}
+
+static int run_decode(FearContext* c, cudaStream_t s, const float* bbox, const float* cls, int B, int apply_sigmoid,
+                      FearBox* boxes) {
+  LaunchScope scope(c, ST_DECODE, s);
+  decode_kernel<<<B, 256, 0, s>>>(bbox, cls, apply_sigmoid, boxes);
+  return check_launch("decode_kernel");
+}
+
+// ------------------------------------------------------------------------------ C ABI
+static bool g_inited = false;
+static int g_device = 0;
+
+extern "C" int fear_abi_version(void) { return FEAR_ABI_VERSION; }
+extern "C" const char* fear_last_error(void) { return g_err; }
+
+extern "C" int fear_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return set_err(FEAR_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_err(FEAR_EINVAL, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp p;
+  CUDA_TRY(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return set_err(FEAR_ENODEV, "device %d is sm_%d%d; libfear_b200 is built for sm_100a only", device, p.major, p.minor);
+  CUDA_TRY(cudaSetDevice(device));
+  g_device = device;
+  g_inited = true;
+  return tc::init();
+}
+
+extern "C" int fear_weight_count(void) { return (int)weight_table().size(); }
+extern "C" const char* fear_weight_name(int i) {
+  if (i < 0 || i >= fear_weight_count()) return nullptr;
+  return weight_table()[i].name.c_str();
+}
+extern "C" int64_t fear_weight_numel(int i) {
+  if (i < 0 || i >= fear_weight_count()) return -1;
+  return weight_table()[i].numel;
+}
+extern "C" int fear_stage_count(void) { return ST_COUNT; }
+extern "C" const char* fear_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : nullptr; }
+
+extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int n, FearContext** handle) {
+  if (!g_inited) return set_err(FEAR_ESTATE, "fear_init() has not been called");
+  if (!blob || !offsets || !handle) return set_err(FEAR_EINVAL, "null argument");
+  const auto& table = weight_table();
+  if (n != (int)table.size()) return set_err(FEAR_EINVAL, "expected %d tensors, got %d", (int)table.size(), n);
+  for (int i = 0; i < n; ++i)
+    if ((int64_t)(offsets[i + 1] - offsets[i]) != table[i].numel)
+      return set_err(FEAR_EINVAL, "tensor %d (%s): expected %lld elements, got %lld", i, table[i].name.c_str(),
+                     (long long)table[i].numel, (long long)(offsets[i + 1] - offsets[i]));
+
+  // Device arena: every tensor 256-byte aligned; depthwise [C][k][k] -> [k*k][C], stem -> [27][16].
+  std::vector<float> arena;
+  std::vector<size_t> dev_off(n);
+  for (int i = 0; i < n; ++i) {
+    size_t o = (arena.size() + 63) & ~(size_t)63;
+    arena.resize(o + table[i].numel, 0.f);
+    dev_off[i] = o;
+    const float* src = blob + offsets[i];
+    const std::string& nm = table[i].name;
+    const bool is_dw = nm.size() > 5 && nm.compare(nm.size() - 5, 5, ".dw.w") == 0;
+    if (nm == "stem.w") {
+      for (int co = 0; co < 16; ++co)
+        for (int t = 0; t < 27; ++t) arena[o + t * 16 + co] = src[co * 27 + t];
+    } else if (is_dw) {
+      // numel = C * kk; kk is 9 or 25.  Find it from the matching bias / table neighbour: C divides numel.
+      int kk = 9;
+      const bool head = nm.find("xif") == std::string::npos;
+      if (!head) {
+        for (const IrfSpec& b : kBlocks)
+          if (nm == std::string(b.name) + ".dw.w") kk = b.k * b.k;
+      }
+      const int64_t C = table[i].numel / kk;
+      for (int64_t ch = 0; ch < C; ++ch)
+        for (int t = 0; t < kk; ++t) arena[o + (int64_t)t * C + ch] = src[ch * kk + t];
+    } else {
+      memcpy(&arena[o], src, sizeof(float) * table[i].numel);
+    }
+  }
+  arena.resize((arena.size() + 63) & ~(size_t)63, 0.f);
+
+  FearContext* c = new FearContext();
+  c->device = g_device;
+  c->opt = g_default_options;
+  cudaError_t e = cudaMalloc(&c->d_weights, arena.size() * sizeof(float));
+  if (e != cudaSuccess) {
+    delete c;
+    return set_err(FEAR_ENOMEM, "cudaMalloc(weights) failed: %s", cudaGetErrorString(e));
+  }
+  e = cudaMemcpy(c->d_weights, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(c->d_weights);
+    delete c;
+    return set_err((int)e, "cudaMemcpy(weights) failed: %s", cudaGetErrorString(e));
+  }
+  int idx = 0;
+  auto next = [&]() { return (const float*)(c->d_weights + dev_off[idx++]); };
+  c->stem_w = next();
+  c->stem_b = next();
+  for (int i = 0; i < kNumBlocks; ++i) {
+    const IrfSpec& sp = kBlocks[i];
+    BlockW& b = c->blocks[i];
+    if (sp.has_pw()) {
+      b.pw.w = next();
+      b.pw.b = next();
+      b.pw.cin = sp.cin;
+      b.pw.cout = sp.mid();
+    }
+    b.dw.w = next();
+    b.dw.b = next();
+    b.dw.c = sp.mid();
+    b.dw.k = sp.k;
+    b.pwl.w = next();
+    b.pwl.b = next();
+    b.pwl.cin = sp.mid();
+    b.pwl.cout = sp.cout;
+  }
+  c->neck.w = next();
+  c->neck.b = next();
+  c->neck.cin = kBackboneC;
+  c->neck.cout = kFeatC;
+  for (int br = 0; br < 2; ++br) {
+    BranchW& w = c->branch[br];
+    w.enc_dw = {next(), nullptr, kFeatC, 3};
+    w.enc_pw.w = next();
+    w.enc_pw.b = next();
+    w.enc_pw.cin = kFeatC;
+    w.enc_pw.cout = kFeatC;
+    w.corr_dw = {next(), nullptr, kCatC, 3};
+    w.corr_pw.w = next();
+    w.corr_pw.b = next();
+    w.corr_pw.cin = kCatC;
+    w.corr_pw.cout = kFeatC;
+  }
+  for (int t = 0; t < 2; ++t)
+    for (int i = 0; i < 2; ++i) {
+      c->tower[t].dw[i] = {next(), nullptr, kFeatC, 3};
+      c->tower[t].pw[i].w = next();
+      c->tower[t].pw[i].b = next();
+      c->tower[t].pw[i].cin = kFeatC;
+      c->tower[t].pw[i].cout = kFeatC;
+    }
+  for (int t = 0; t < 2; ++t) {
+    c->pred_dw[t] = {next(), nullptr, kFeatC, 3};
+    c->pred_w[t] = next();
+    c->pred_b[t] = next();
+  }
+  if (idx != n) {
+    cudaFree(c->d_weights);
+    delete c;
+    return set_err(FEAR_ESTATE, "internal: weight table walk consumed %d of %d tensors", idx, n);
+  }
+  *handle = c;
+  int r = fear_reserve(c, 1);
+  if (r) {
+    fear_free(c);
+    *handle = nullptr;
+  }
+  return r;
+}
+
+extern "C" int fear_reserve(FearContext* c, int max_batch) {
+  if (!c) return set_err(FEAR_ESTATE, "null handle");
+  if (max_batch < 1) return set_err(FEAR_EINVAL, "max_batch must be >= 1");
+  if (max_batch <= c->reserved) return 0;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (c->ws) cudaFree(c->ws);
+  c->ws = nullptr;
+  c->reserved = 0;
+  const int64_t per_frame[] = {
+      kActX, kActX, kActE, kActD,                                   // bufX bufY bufE bufD
+      (int64_t)kScorePix * kFeatC,                                  // hF
+      (int64_t)kScorePix * kCatC,                                   // hT
+      (int64_t)kScorePix * kCatC, (int64_t)kScorePix * kCatC,       // hCAT[2]
+      (int64_t)kScorePix * kFeatC, (int64_t)kScorePix * kFeatC,     // hD[2]
+      (int64_t)kScorePix * kFeatC,                                  // hP
+      (int64_t)kScorePix * kFeatC, (int64_t)kScorePix * kFeatC,     // hQ[2]
+      (int64_t)kTmplPix * kFeatC,                                   // zt
+      4 * kScorePix, kScorePix,                                     // mapB mapC
+  };
+  int64_t total = 0;
+  std::vector<int64_t> offs;
+  for (int64_t pf : per_frame) {
+    offs.push_back(total);
+    total += ((pf * max_batch + 63) / 64) * 64;
+  }
+  cudaError_t e = cudaMalloc(&c->ws, (size_t)total * sizeof(float));
+  if (e != cudaSuccess)
+    return set_err(FEAR_ENOMEM, "workspace cudaMalloc(%lld MB) failed: %s", (long long)(total * 4 >> 20),
+                   cudaGetErrorString(e));
+  float* p = c->ws;
+  c->bufX = p + offs[0];
+  c->bufY = p + offs[1];
+  c->bufE = p + offs[2];
+  c->bufD = p + offs[3];
+  c->hF = p + offs[4];
+  c->hT = p + offs[5];
+  c->hCAT[0] = p + offs[6];
+  c->hCAT[1] = p + offs[7];
+  c->hD[0] = p + offs[8];
+  c->hD[1] = p + offs[9];
+  c->hP = p + offs[10];
+  c->hQ[0] = p + offs[11];
+  c->hQ[1] = p + offs[12];
+  c->zt = p + offs[13];
+  c->mapB = p + offs[14];
+  c->mapC = p + offs[15];
+  c->reserved = max_batch;
+  return 0;
+}
+
+extern "C" void fear_free(FearContext* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  for (auto& ev : c->events) {
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  if (c->ws) cudaFree(c->ws);
+  if (c->d_weights) cudaFree(c->d_weights);
+  delete c;
+}
+
+static int check_ctx(FearContext* c) {
+  if (!c || !c->d_weights || !c->ws) return set_err(FEAR_ESTATE, "handle not initialised");
+  return 0;
+}
+
+extern "C" int fear_get_features(FearContext* c, const float* d_img, int B, int H, int W, float* d_feat, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_img || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
+    return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = (H / 16) * (W / 16);
+  for (int b0 = 0; b0 < B; b0 += c->reserved) {
+    const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
+    FEAR_TRY(run_features(c, s, d_img + (long long)b0 * 3 * H * W, nb, H, W, c->hF));
+    FEAR_TRY(launch_transpose(c, s, c->hF, kFeatC, (long long)P * kFeatC, d_feat + (long long)b0 * kFeatC * P, P,
+                              (long long)kFeatC * P, P, kFeatC, nb));
+  }
+  return 0;
+}
+
+extern "C" int fear_backbone(FearContext* c, const float* d_img, int B, int H, int W, float* d_feat, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_img || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
+    return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = (H / 16) * (W / 16);
+  for (int b0 = 0; b0 < B; b0 += c->reserved) {
+    const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
+    const float* X = nullptr;
+    FEAR_TRY(run_backbone(c, s, d_img + (long long)b0 * 3 * H * W, nb, H, W, &X));
+    FEAR_TRY(launch_transpose(c, s, X, kBackboneC, (long long)P * kBackboneC, d_feat + (long long)b0 * kBackboneC * P,
+                              P, (long long)kBackboneC * P, P, kBackboneC, nb));
+  }
+  return 0;
+}
+
+// zfeat NCHW (Bz,256,8,8) -> c->zt chunk [nz][64][256]
+static int stage_template(FearContext* c, cudaStream_t s, const float* d_zfeat, int nz) {
+  return launch_transpose(c, s, d_zfeat, kTmplPix, (long long)kFeatC * kTmplPix, c->zt, kFeatC,
+                          (long long)kTmplPix * kFeatC, kFeatC, kTmplPix, nz);
+}
+
+extern "C" int fear_head(FearContext* c, const float* d_zfeat, int Bz, const float* d_xfeat, int B, float* d_bbox,
+                         float* d_cls, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_zfeat || !d_xfeat || !d_bbox || !d_cls || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Bz == 1) FEAR_TRY(stage_template(c, s, d_zfeat, 1));
+  for (int b0 = 0; b0 < B; b0 += c->reserved) {
+    const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
+    if (Bz != 1) FEAR_TRY(stage_template(c, s, d_zfeat + (long long)b0 * kFeatC * kTmplPix, nb));
+    FEAR_TRY(launch_transpose(c, s, d_xfeat + (long long)b0 * kFeatC * kScorePix, kScorePix,
+                              (long long)kFeatC * kScorePix, c->hF, kFeatC, (long long)kScorePix * kFeatC, kFeatC,
+                              kScorePix, nb));
+    FEAR_TRY(run_head(c, s, c->zt, Bz == 1 ? 1 : nb, c->hF, nb, d_bbox + (long long)b0 * 4 * kScorePix,
+                      d_cls + (long long)b0 * kScorePix));
+  }
+  return 0;
+}
+
+static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, const float* d_search,
+                      const float* d_zfeat, int Bz, int B, float* d_bbox, float* d_cls, FearBox* d_boxes) {
+  if (d_zfeat && Bz == 1) FEAR_TRY(stage_template(c, s, d_zfeat, 1));
+  for (int b0 = 0; b0 < B; b0 += c->reserved) {
+    const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
+    int nz = nb;
+    if (d_template) {
+      // template branch writes NHWC [nb][64][256] straight into zt (= the correlation kernel's layout)
+      FEAR_TRY(run_features(c, s, d_template + (long long)b0 * 3 * 128 * 128, nb, 128, 128, c->zt));
+    } else if (Bz != 1) {
+      FEAR_TRY(stage_template(c, s, d_zfeat + (long long)b0 * kFeatC * kTmplPix, nb));
+    } else {
+      nz = 1;
+    }
+    FEAR_TRY(run_features(c, s, d_search + (long long)b0 * 3 * 256 * 256, nb, 256, 256, c->hF));
+    float* bb = d_bbox ? d_bbox + (long long)b0 * 4 * kScorePix : c->mapB;
+    float* cc = d_cls ? d_cls + (long long)b0 * kScorePix : c->mapC;
+    FEAR_TRY(run_head(c, s, c->zt, nz, c->hF, nb, bb, cc));
+    if (d_boxes) FEAR_TRY(run_decode(c, s, bb, cc, nb, 1, d_boxes + b0));
+  }
+  return 0;
+}
+
+extern "C" int fear_track(FearContext* c, const float* d_search, const float* d_zfeat, int Bz, int B, float* d_bbox,
+                          float* d_cls, FearBox* d_boxes, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_search || !d_zfeat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
+  return track_impl(c, (cudaStream_t)stream, nullptr, d_search, d_zfeat, Bz, B, d_bbox, d_cls, d_boxes);
+}
+
+extern "C" int fear_forward(FearContext* c, const float* d_template, const float* d_search, int B, float* d_bbox,
+                            float* d_cls, FearBox* d_boxes, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_template || !d_search || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
+  return track_impl(c, (cudaStream_t)stream, d_template, d_search, nullptr, B, B, d_bbox, d_cls, d_boxes);
+}
+
+extern "C" int fear_decode(const float* d_bbox, const float* d_cls, int B, int apply_sigmoid, FearBox* d_boxes,
+                           void* stream) {
+  if (!d_bbox || !d_cls || !d_boxes || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  return run_decode(nullptr, (cudaStream_t)stream, d_bbox, d_cls, B, apply_sigmoid, d_boxes);
+}
+
+extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream) {
+  if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B);
+}
+
+// Scratch for the handle-less NCHW wrapper; grows (cudaMalloc) only when a larger batch arrives.
+static float* g_scratch = nullptr;
+static size_t g_scratch_floats = 0;
+
+extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* stream) {
+  if (!d_z || !d_x || !d_out || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t need = (size_t)B * kScorePix * kCatC + (size_t)Bz * kCorrC * kFeatC;
+  if (need > g_scratch_floats) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr;
+    g_scratch_floats = 0;
+    CUDA_TRY(cudaMalloc(&g_scratch, need * sizeof(float)));
+    g_scratch_floats = need;
+  }
+  float* cat = g_scratch;
+  float* zt = g_scratch + (size_t)B * kScorePix * kCatC;
+  // z [c][k] -> zt [k][c];  x [c][p] -> cat[p][0:256]
+  FEAR_TRY(launch_transpose(nullptr, s, d_z, kCorrC, (long long)kFeatC * kCorrC, zt, kFeatC, (long long)kCorrC * kFeatC,
+                            kFeatC, kCorrC, Bz));
+  FEAR_TRY(launch_transpose(nullptr, s, d_x, kScorePix, (long long)kFeatC * kScorePix, cat, kCatC,
+                            (long long)kScorePix * kCatC, kFeatC, kScorePix, B));
+  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B));
+  // cat [p][320] -> out [320][p]
+  return launch_transpose(nullptr, s, cat, kCatC, (long long)kScorePix * kCatC, d_out, kScorePix,
+                          (long long)kCatC * kScorePix, kScorePix, kCatC, B);
+}
+
+// ---- debug / introspection of intermediates (tests localise a mismatch with these) ----------
+extern "C" int fear_debug_backbone_prefix(FearContext* c, const float* d_img, int B, int H, int W, int nblocks,
+                                          float* d_out, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_img || !d_out || B < 1 || B > c->reserved || nblocks < 0 || nblocks > kNumBlocks)
+    return set_err(FEAR_EINVAL, "bad argument (B must be <= reserved batch)");
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    LaunchScope scope(c, ST_STEM, s);
+    const long long total = (long long)B * (H / 2) * (W / 2);
+    stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_img, c->stem_w, c->stem_b, c->bufX, B, H, W);
+    FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
+  }
+  int h = H / 2, w = W / 2, ch = kStemC;
+  float *X = c->bufX, *Y = c->bufY;
+  for (int i = 0; i < nblocks; ++i) {
+    const IrfSpec& sp = kBlocks[i];
+    const BlockW& bw = c->blocks[i];
+    const float* E = X;
+    if (sp.has_pw()) {
+      FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), B * h * w, 1));
+      E = c->bufE;
+    }
+    FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
+    h /= sp.stride;
+    w /= sp.stride;
+    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, Y,
+                       sp.cout, B * h * w, 0));
+    float* t = X;
+    X = Y;
+    Y = t;
+    ch = sp.cout;
+  }
+  const int P = h * w;
+  return launch_transpose(c, s, X, ch, (long long)P * ch, d_out, P, (long long)ch * P, P, ch, B);
+}
+
+// Copy a head intermediate of the LAST run (first B frames) out as NCHW (B, C, 16, 16).
+extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, float* d_out, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!name || !d_out || B < 1 || B > c->reserved) return set_err(FEAR_EINVAL, "bad argument");
+  const float* src = nullptr;
+  int ch = kFeatC;
+  if (!strcmp(name, "cat_cls")) src = c->hCAT[0], ch = kCatC;
+  else if (!strcmp(name, "cat_reg")) src = c->hCAT[1], ch = kCatC;
+  else if (!strcmp(name, "cls_dw")) src = c->hD[0];
+  else if (!strcmp(name, "reg_dw")) src = c->hD[1];
+  else if (!strcmp(name, "x_reg")) src = c->hQ[0];
+  else if (!strcmp(name, "cls_tower")) src = c->hQ[1];
+  else if (!strcmp(name, "search_features")) src = c->hF;
+  else return set_err(FEAR_EINVAL, "unknown head tensor '%s'", name);
+  return launch_transpose(c, (cudaStream_t)stream, src, ch, (long long)kScorePix * ch, d_out, kScorePix,
+                          (long long)ch * kScorePix, kScorePix, ch, B);
+}
+
+extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
+  if (!key || !value) return set_err(FEAR_EINVAL, "null option");
+  Options& o = c ? c->opt : g_default_options;
+  int impl;
+  if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
+  else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;
+  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (ffma | tcgen05)", value);
+  if (impl == IMPL_TC && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
+  if (!strcmp(key, "corr")) o.corr = impl;
+  else if (!strcmp(key, "pw")) o.pw = impl;
+  else return set_err(FEAR_EINVAL, "unknown option '%s' (corr | pw)", key);
+  return 0;
+}
+
+extern "C" int64_t fear_launch_count(const FearContext* c) { return c ? c->launches : 0; }
+
+extern "C" int fear_profile(FearContext* c, int enable) {
+  FEAR_TRY(check_ctx(c));
+  if (enable && c->events.empty()) {
+    c->events.resize(8192);
+    for (auto& ev : c->events) {
+      CUDA_TRY(cudaEventCreate(&ev.a));
+      CUDA_TRY(cudaEventCreate(&ev.b));
+    }
+  }
+  c->profiling = enable != 0;
+  c->events_used = 0;
+  for (int i = 0; i < ST_COUNT; ++i) {
+    c->stage_ms[i] = 0;
+    c->stage_launches[i] = 0;
+  }
+  return 0;
+}
+
+extern "C" int fear_stage_ms(FearContext* c, int i, float* ms, int64_t* launches) {
+  FEAR_TRY(check_ctx(c));
+  if (i < 0 || i >= ST_COUNT) return set_err(FEAR_EINVAL, "stage index out of range");
+  if (c->events_used) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (size_t k = 0; k < c->events_used; ++k) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, c->events[k].a, c->events[k].b));
+      c->stage_ms[c->events[k].stage] += t;
+    }
+    c->events_used = 0;
+  }
+  if (ms) *ms = (float)c->stage_ms[i];
+  if (launches) *launches = c->stage_launches[i];
+  return 0;
+}

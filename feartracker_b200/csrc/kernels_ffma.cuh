@@ -1,0 +1,318 @@
+// CUDA-core (FFMA) kernels of the FEAR-XS hot path, channels-last (NHWC) fp32.
+//
+// These are the always-correct implementations every stage can run on; the tcgen05 kernels in
+// kernels_tc.cuh replace the dense contractions (1x1 convs, correlation) where they apply.
+// Layout: activations [B][H][W][C] fp32, C a multiple of 4 (float4 over channels); 1x1 weights
+// torch-native [Cout][Cin] ("K-major"); depthwise weights [k*k][C]; stem weights [27][16].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fear_b200.h"
+
+namespace fear {
+
+// ------------------------------------------------------------------------------------------
+// Stem: conv3x3 stride 2 pad 1, 3 -> 16, + folded BN bias + ReLU.   NCHW in -> NHWC out.
+// (fbnet_c xif0_0; reference call site fear_net.py:58-61.)  One thread per output pixel, all 16
+// output channels in registers; the 432 weights are broadcast from shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stem_conv3x3s2_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int B, int H, int W) {
+  __shared__ float sw[27 * 16];
+  __shared__ float sb[16];
+  for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wo);
+  const int oy = (int)((idx / Wo) % Ho);
+  const int b = (int)(idx / ((long long)Wo * Ho));
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = sb[c];
+  const float* base = img + (long long)b * 3 * H * W;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(base + ((long long)ci * H + iy) * W + ix);
+        const float* wr = sw + (ci * 9 + ky * 3 + kx) * 16;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+      }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(out + idx * 16);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    o[q] = make_float4(fmaxf(acc[4 * q], 0.f), fmaxf(acc[4 * q + 1], 0.f), fmaxf(acc[4 * q + 2], 0.f),
+                       fmaxf(acc[4 * q + 3], 0.f));
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise KxK conv (pad K/2, stride S) NHWC, optional bias / ReLU.  One thread per
+// (pixel, 4 channels): neighbouring threads walk the channel dimension => 16-byte coalesced
+// loads; the K*K taps of a pixel hit L1 (each input value is reused by up to K*K/S^2 outputs).
+// Backbone dw (+BN+ReLU): mobile_cv IRF block; head dw: SepConv.depthwise, blocks.py:57-66.
+// ------------------------------------------------------------------------------------------
+template <int K, int S, bool RELU, bool BIAS>
+__global__ void __launch_bounds__(256) dw_conv_nhwc_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
+                                                           const float4* __restrict__ bias, float4* __restrict__ out,
+                                                           int B, int H, int W, int C4) {
+  const int Ho = H / S, Wo = W / S;
+  const long long total = (long long)B * Ho * Wo * C4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const long long pix = idx / C4;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int b = (int)(pix / ((long long)Wo * Ho));
+  constexpr int P = K / 2;
+  float4 acc = BIAS ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* inb = in + (long long)b * H * W * C4;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = oy * S - P + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const int ix = ox * S - P + kx;
+      if (ix < 0 || ix >= W) continue;
+      const float4 v = __ldg(inb + ((long long)iy * W + ix) * C4 + c4);
+      const float4 k = __ldg(w + (ky * K + kx) * C4 + c4);
+      acc.x = fmaf(v.x, k.x, acc.x);
+      acc.y = fmaf(v.y, k.y, acc.y);
+      acc.z = fmaf(v.z, k.z, acc.z);
+      acc.w = fmaf(v.w, k.w, acc.w);
+    }
+  }
+  if (RELU) {
+    acc.x = fmaxf(acc.x, 0.f);
+    acc.y = fmaxf(acc.y, 0.f);
+    acc.z = fmaxf(acc.z, 0.f);
+    acc.w = fmaxf(acc.w, 0.f);
+  }
+  out[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1x1 conv / correlation as a GEMM on CUDA cores:  C[M][N] = A[M][K] * Bw[N][K]^T (+bias)(+R)(ReLU)
+// A rows = pixels (lda floats apart), Bw rows = output channels (ldb apart), both K-contiguous.
+// Tile 128 x BN x 16, 256 threads as 32 (rows, 4 each) x 8 (cols, TN = BN/8 each).
+// gridDim.z batches independent problems (per-frame correlation: A/C strided per frame, Bw
+// strided per frame or shared when strideB == 0 -- template batch-1 broadcast, blocks.py:123).
+// ------------------------------------------------------------------------------------------
+template <int TN>
+__global__ void __launch_bounds__(256) gemm_nt_ffma_kernel(const float* __restrict__ A, int lda, long long strideA,
+                                                           const float* __restrict__ Bw, int ldb, long long strideB,
+                                                           const float* __restrict__ bias, const float* __restrict__ R,
+                                                           int ldr, float* __restrict__ C, int ldc, long long strideC,
+                                                           int M, int N, int K, int relu) {
+  constexpr int BM = 128, BK = 16, BN = 8 * TN, TM = 4;
+  constexpr int AS = BM + 4;  // padded row length of the k-major A tile
+  __shared__ __align__(16) float As[BK][AS];
+  __shared__ __align__(16) float Bs[BK][BN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  A += (long long)blockIdx.z * strideA;
+  Bw += (long long)blockIdx.z * strideB;
+  C += (long long)blockIdx.z * strideC;
+  if (R) R += (long long)blockIdx.z * strideC;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A tile: 128 rows x 16 k = 512 float4, two per thread; stored transposed (k-major).
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int id = tid + it * 256;
+      const int r = id >> 2, kq = (id & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && k0 + kq < K) v = __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + kq));
+      As[kq + 0][r] = v.x;
+      As[kq + 1][r] = v.y;
+      As[kq + 2][r] = v.z;
+      As[kq + 3][r] = v.w;
+    }
+    // B tile: BN rows (output channels) x 16 k.
+    for (int id = tid; id < BN * 4; id += 256) {
+      const int n = id >> 2, kq = (id & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + n < N && k0 + kq < K) v = __ldg(reinterpret_cast<const float4*>(Bw + (long long)(n0 + n) * ldb + k0 + kq));
+      Bs[kq + 0][n] = v.x;
+      Bs[kq + 1][n] = v.y;
+      Bs[kq + 2][n] = v.z;
+      Bs[kq + 3][n] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+      const float a[TM] = {a4.x, a4.y, a4.z, a4.w};
+      float bv[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int row = m0 + ty * TM + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int col = n0 + tx * TN + j;
+      if (col >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += __ldg(bias + col);
+      if (R) v += __ldg(R + (long long)row * ldr + col);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(long long)row * ldc + col] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched 2-D transpose with leading dimensions: out[b][j][i] = in[b][i][j], i < R, j < Cn.
+// Used for NCHW <-> NHWC at the API boundary (the reference API is NCHW, fear_net.py:58-96).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ldin, long long strideIn,
+                                                        float* __restrict__ out, int ldout, long long strideOut, int R,
+                                                        int Cn) {
+  __shared__ float tile[32][33];
+  in += (long long)blockIdx.z * strideIn;
+  out += (long long)blockIdx.z * strideOut;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < R && c < Cn) tile[i][tx] = in[(long long)r * ldin + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < Cn) out[(long long)c * ldout + r] = tile[tx][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Prediction 1x1 conv (256 -> NOUT, NOUT = 4 | 1) fused with the BoxTower epilogue
+// (blocks.py:187-188,192):  bbox = exp(adjust * pred + bias), cls = 0.1 * pred.  adjust / 0.1 /
+// biases are folded into w, b on the host, so this is  out = f(w . t + b).  One warp per pixel,
+// NHWC in, NCHW out (B, NOUT, 16, 16) -- the layout FEARNet returns.
+// ------------------------------------------------------------------------------------------
+template <int NOUT, bool EXP>
+__global__ void __launch_bounds__(256) pred_pw_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float* __restrict__ out, int B) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * 256) return;
+  const float4* tp = reinterpret_cast<const float4*>(t + (long long)warp * 256);
+  const float4 v0 = __ldg(tp + lane), v1 = __ldg(tp + 32 + lane);
+  float acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    const float4* wp = reinterpret_cast<const float4*>(w + o * 256);
+    const float4 w0 = __ldg(wp + lane), w1 = __ldg(wp + 32 + lane);
+    float s = v0.x * w0.x;
+    s = fmaf(v0.y, w0.y, s);
+    s = fmaf(v0.z, w0.z, s);
+    s = fmaf(v0.w, w0.w, s);
+    s = fmaf(v1.x, w1.x, s);
+    s = fmaf(v1.y, w1.y, s);
+    s = fmaf(v1.z, w1.z, s);
+    s = fmaf(v1.w, w1.w, s);
+    acc[o] = s;
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+  if (lane < NOUT) {
+    float v = 0.f;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+      if (lane == o) v = acc[o];
+    v += __ldg(b + lane);
+    if (EXP) v = expf(v);
+    const int frame = warp >> 8, p = warp & 255;
+    out[((long long)frame * NOUT + lane) * 256 + p] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Box decode (FEARTracker._postprocess + FEARBoxCoder.decode, fear_tracker.py:74-86,
+// box_coder.py:75-107): score = sigmoid(cls) in fp32, argmax = first maximum in row-major
+// order, box = [gx - l, gy - t, (gx + r) - (gx - l), (gy + b) - (gy - t)] evaluated in double
+// (the reference's grid is float64, utils/utils.py:183-199, so torch promotes).  One 256-thread
+// block per frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ bbox, const float* __restrict__ cls,
+                                                     int apply_sigmoid, FearBox* __restrict__ boxes) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int f = blockIdx.x, t = threadIdx.x;
+  float v = cls[(long long)f * 256 + t];
+  if (apply_sigmoid) v = 1.0f / (1.0f + expf(-v));
+  int i = t;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, d);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, d);
+    if (ov > v || (ov == v && oi < i)) {
+      v = ov;
+      i = oi;
+    }
+  }
+  if ((t & 31) == 0) {
+    sv[t >> 5] = v;
+    si[t >> 5] = i;
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int k = 1; k < 8; ++k)
+      if (sv[k] > v || (sv[k] == v && si[k] < i)) {
+        v = sv[k];
+        i = si[k];
+      }
+    const int r = i >> 4, c = i & 15;
+    const double gx = (double)((c - 8) * 16 + 128), gy = (double)((r - 8) * 16 + 128);
+    const float* bb = bbox + (long long)f * 4 * 256 + i;
+    const double x1 = gx - (double)bb[0], y1 = gy - (double)bb[256];
+    const double x2 = gx + (double)bb[512], y2 = gy + (double)bb[768];
+    FearBox o;
+    o.x = x1;
+    o.y = y1;
+    o.w = x2 - x1;
+    o.h = y2 - y1;
+    o.score = v;
+    o.row = r;
+    o.col = c;
+    o.flat = i;
+    boxes[f] = o;
+  }
+}
+
+}  // namespace fear

@@ -1,0 +1,156 @@
+"""FEARTracker: stateful single-object tracker around the B200 FEARNet.
+
+API mirror of reference model_training/tracker/base_tracker.py:28-124 and fear_tracker.py:13-86:
+``FEARTracker(model, cuda_id=0, **tracking_config)``, ``initialize(image, rect)``,
+``update(image) -> {"bbox": [x, y, w, h]}``, ``track(search_crop)``, ``get_template_features``,
+``to_device``, ``reset``.  Cropping / normalisation stay on the host (cv2 fixed-point resize is part
+of the reference's observable behaviour); network + decode run in libfear_b200 and only the
+48-byte box record comes back per frame.
+"""
+from collections import deque
+from typing import Any, Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import image_ops
+from .box_coder import FEARBoxCoder, TrackerDecodeResult
+from .constants import TARGET_CLASSIFICATION_KEY, TARGET_REGRESSION_LABEL_KEY
+
+
+class TrackingState:
+    def __init__(self) -> None:
+        self.frame_h = 0
+        self.frame_w = 0
+        self.bbox: Optional[np.ndarray] = None
+        self.mapping: Optional[np.ndarray] = None
+        self.prev_size = None
+        self.mean_color = None
+        self.paths = None
+
+    def save_frame_shape(self, frame: np.ndarray) -> None:
+        self.frame_h, self.frame_w = frame.shape[0], frame.shape[1]
+
+
+class Tracker:
+    def __init__(self, model: nn.Module, cuda_id: Union[int, str] = 0, **tracking_config: Any) -> None:
+        self.cuda_id = cuda_id
+        self.tracking_config = tracking_config
+        self.tracking_state = TrackingState()
+        self.net = model
+        self.box_coder = self.get_box_coder(tracking_config, cuda_id)
+        self._template_features = None
+        self.window = self._get_tracking_window(tracking_config["windowing"], tracking_config["score_size"])
+        self.to_device(cuda_id)
+
+    def get_box_coder(self, tracking_config, cuda_id: int = 0):
+        raise NotImplementedError
+
+    def to_device(self, cuda_id) -> None:
+        self.cuda_id = cuda_id
+        self.box_coder = self.box_coder.to_device(cuda_id)
+
+    @staticmethod
+    def _get_tracking_window(windowing: str, score_size: int) -> np.ndarray:
+        if windowing == "cosine":
+            return np.outer(np.hanning(score_size), np.hanning(score_size))
+        return np.ones((int(score_size), int(score_size)))
+
+    def _device(self) -> torch.device:
+        if not torch.cuda.is_available():
+            raise RuntimeError("FEARTracker (B200) needs a CUDA device: there is no CPU path")
+        return torch.device("cuda", self.cuda_id if isinstance(self.cuda_id, int) else 0)
+
+    def _preprocess_image(self, image: np.ndarray, transform=None) -> torch.Tensor:
+        """uint8 HWC crop -> normalised float32 (1,3,H,W) on the tracker's device (pinned staging)."""
+        chw = np.ascontiguousarray(np.transpose(image_ops.normalize(image[:, :, :3]), (2, 0, 1))[None])
+        return torch.from_numpy(chw).pin_memory().to(self._device(), non_blocking=True)
+
+    def _rescale_bbox(self, bbox, padded_box):
+        return image_ops.rescale_bbox(bbox, padded_box, self.tracking_config["instance_size"])
+
+    def reset(self) -> None:
+        self._template_features = None
+
+    def initialize(self, image: np.ndarray, rect: np.ndarray, **kwargs) -> None:
+        pass
+
+    def update(self, image: np.ndarray, *kw) -> Dict[str, Any]:
+        return {"bbox": self.tracking_state.bbox}
+
+
+class FEARTracker(Tracker):
+    def get_box_coder(self, tracking_config, cuda_id: int = 0):
+        return FEARBoxCoder(tracker_config=tracking_config)
+
+    def initialize(self, image: np.ndarray, rect: np.ndarray, **kwargs) -> None:
+        """image: RGB uint8 HxWx3; rect: [x, y, w, h], 0-based."""
+        rect = image_ops.clamp_bbox(rect, image.shape)
+        st = self.tracking_state
+        st.bbox = rect
+        st.paths = deque([rect], maxlen=10)
+        st.mean_color = np.mean(image, axis=(0, 1))
+        self._template_features = self.get_template_features(image, rect)
+
+    def get_template_features(self, image: np.ndarray, rect: np.ndarray) -> torch.Tensor:
+        crop, _, _ = image_ops.extended_crop(image, rect, self.tracking_config["template_size"],
+                                             self.tracking_config["template_bbox_offset"])
+        return self.net.get_features(self._preprocess_image(crop))
+
+    def update(self, image: np.ndarray, *kw) -> Dict[str, Any]:
+        st, cfg = self.tracking_state, self.tracking_config
+        crop, search_bbox, context = image_ops.extended_crop(image, st.bbox, cfg["instance_size"],
+                                                             cfg["search_context"], st.mean_color)
+        st.mapping = context
+        st.prev_size = search_bbox[2:]
+        pred_bbox, _ = self.track(crop)
+        pred_bbox = image_ops.clamp_bbox(self._rescale_bbox(pred_bbox, context), image.shape)
+        st.bbox = pred_bbox
+        st.paths.append(pred_bbox)
+        return dict(bbox=pred_bbox)
+
+    def track(self, search_crop: np.ndarray) -> Tuple[np.ndarray, float]:
+        search = self._preprocess_image(search_crop)
+        if self.tracking_config.get("smooth", False):
+            return self._postprocess(self.net.track(search, self._template_features))
+        rec = self.net.boxes_to_numpy(self.net.track_boxes(search, self._template_features))[0]
+        return np.array([rec["x"], rec["y"], rec["w"], rec["h"]]), np.float32(rec["score"])
+
+    # -- reference-shaped post-processing on a maps dictionary (used for the optional smoothing) --
+    def _postprocess(self, track_result: Dict[str, torch.Tensor]) -> Tuple[np.ndarray, float]:
+        reg = track_result[TARGET_REGRESSION_LABEL_KEY].detach().float()
+        cls_score = track_result[TARGET_CLASSIFICATION_KEY].detach().float().sigmoid()
+        if not self.tracking_config.get("smooth", False):
+            rec = self.box_coder.decode_records(reg, cls_score, use_sigmoid=False)[0]
+            return np.array([rec["x"], rec["y"], rec["w"], rec["h"]]), np.float32(rec["score"])
+        return self._smooth_postprocess(reg.cpu().numpy()[0].astype(np.float64), cls_score.cpu().numpy()[0, 0])
+
+    def _smooth_postprocess(self, reg: np.ndarray, score: np.ndarray) -> Tuple[np.ndarray, float]:
+        """Scale/ratio penalty + cosine window + size smoothing (reference base_tracker.py:126-205),
+        256-element float64 host math; only active when the config carries ``smooth: true``."""
+        cfg, st = self.tracking_config, self.tracking_state
+        gx, gy = self.box_coder.grid_x.cpu().numpy()[0], self.box_coder.grid_y.cpu().numpy()[0]
+        x1, y1, x2, y2 = gx - reg[0], gy - reg[1], gx + reg[2], gy + reg[3]
+
+        def limit(r):
+            return np.maximum(r, 1.0 / r)
+
+        def sq(w, h):
+            pad = (w + h) * 0.5
+            return np.sqrt((w + pad) * (h + pad))
+
+        pw, ph = st.prev_size
+        s_c = limit(sq(x2 - x1, y2 - y1) / sq(pw, ph))
+        r_c = limit((pw / ph) / ((x2 - x1) / (y2 - y1)))
+        penalty = np.exp(-(r_c * s_c - 1) * cfg["penalty_k"])
+        pscore = penalty * score
+        pscore = pscore * (1 - cfg["window_influence"]) + self.window * cfg["window_influence"]
+        flat = int(np.argmax(pscore))
+        r, c = flat // 16, flat % 16
+        box = np.array([x1[r, c], y1[r, c], x2[r, c] - x1[r, c], y2[r, c] - y1[r, c]])
+        lr = float(penalty[r, c] * score[r, c] * cfg["lr"])
+        size, prev = box[2:] * lr, np.asarray(st.prev_size) * (1 - lr)
+        w = prev[0] + lr * (size[0] + prev[0])
+        h = prev[1] + lr * (size[1] + prev[1])
+        return np.array([box[0], box[1], w, h]), score[r, c]

@@ -1,0 +1,140 @@
+/* fear_b200.h -- C ABI of libfear_b200.so: the B200-native (sm_100a) FEAR-XS per-frame
+ * inference hot path (backbone -> pixel-wise correlation -> cls/reg heads -> box decode).
+ *
+ * The reference (PinataFarms/FEARTracker) is pure Python/PyTorch and has no FFI; these entry
+ * points are what a binding for its hot path replaces (file:line relative to the reference):
+ *
+ *   fear_get_features     FEARNet.get_features            model_training/model/fear_net.py:63-66
+ *                         (= Encoder stages 0..17 + AdjustLayer, blocks.py:8-42,75-88)
+ *   fear_backbone         FEARNet.feature_extractor       model_training/model/fear_net.py:58-61
+ *   fear_head             FEARNet.connector / BoxTower.forward  fear_net.py:76-81, blocks.py:174-194
+ *   fear_track            FEARNet.track (+ FEARTracker._postprocess / FEARBoxCoder.decode)
+ *                         fear_net.py:90-96, tracker/fear_tracker.py:74-86, dataset/box_coder.py:75-107
+ *   fear_forward          FEARNet.forward((template, search))   fear_net.py:83-88
+ *   fear_corr_concat_f32  MobileCorrelation.forward front half (matmul + cat)  blocks.py:121-124
+ *   fear_corr_nhwc_f32    same contraction on the library's internal channels-last layout
+ *   fear_decode           FEARBoxCoder.decode                 dataset/box_coder.py:75-107
+ *   fear_pack_weights     load_from_lighting + nn.Module.load_state_dict  utils/torch.py:11-24
+ *
+ * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (torch keeps
+ * ownership); tensors are dense fp32 in the reference's NCHW layout unless stated; `stream`
+ * is a cudaStream_t passed as void*.  Calls are asynchronous on `stream`, never synchronise
+ * it and never allocate (workspace is reserved up front by fear_reserve; a batch larger than
+ * the reservation is processed in chunks).  Return 0 on success, a positive cudaError_t or a
+ * negative FEAR_E* code otherwise; fear_last_error() gives the message (thread-local).
+ * Handles are not thread-safe: one handle per host thread / stream.
+ */
+#ifndef FEAR_B200_H
+#define FEAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEAR_ABI_VERSION 1
+
+#define FEAR_EINVAL (-1)    /* bad argument (shape, null pointer, alignment)            */
+#define FEAR_ESTATE (-2)    /* handle not initialised / weights not packed              */
+#define FEAR_ENOMEM (-3)    /* workspace reservation failed                             */
+#define FEAR_ENODEV (-4)    /* no sm_100 device                                         */
+
+#define FEAR_FEAT_CH 256        /* AdjustLayer output channels                          */
+#define FEAR_SCORE 16           /* score map side (256 / 16)                            */
+#define FEAR_TMPL 8             /* template feature side (128 / 16)                     */
+#define FEAR_CORR_CH 64         /* FEAR_TMPL^2 correlation channels                     */
+
+/* One decoded frame (FEARBoxCoder.decode semantics: xywh in float64 like the reference,
+ * which promotes to double through its float64 grid; (row, col) = unravel(argmax)). */
+typedef struct FearBox {
+  double x, y, w, h;
+  float score;      /* sigmoid(cls)[row, col]                                           */
+  int32_t row, col; /* argmax of sigmoid(cls), first maximum in row-major order         */
+  int32_t flat;     /* row * 16 + col                                                   */
+} FearBox;
+
+typedef struct FearContext FearContext;
+
+/* Select the device and verify it is sm_100.  Call once per process before anything else. */
+int fear_init(int device);
+int fear_abi_version(void);
+const char* fear_last_error(void);
+
+/* ---- weights ------------------------------------------------------------------------
+ * The library owns the canonical list of (BN-folded) tensors it needs; the host packs them
+ * in that order into one fp32 blob.  Names look like "xif4_5.pw.w"; shapes are torch-native
+ * ([Cout][Cin] for 1x1, [C][k][k] for depthwise, [16][3][3][3] for the stem). */
+int fear_weight_count(void);
+const char* fear_weight_name(int i);
+int64_t fear_weight_numel(int i);
+
+/* blob: HOST pointer to the packed fp32 tensors; offsets[i] = element offset of tensor i,
+ * offsets[n] = total elements; n must equal fear_weight_count().  Creates *handle. */
+int fear_pack_weights(const float* blob, const uint64_t* offsets, int n, FearContext** handle);
+/* Reserve device workspace for batches up to max_batch search frames (default 1). */
+int fear_reserve(FearContext* h, int max_batch);
+void fear_free(FearContext* h);
+
+/* ---- hot path -----------------------------------------------------------------------*/
+/* img (B,3,H,W) -> feat (B,256,H/16,W/16);  H, W multiples of 16, <= 256. */
+int fear_get_features(FearContext* h, const float* d_img, int B, int H, int W, float* d_feat, void* stream);
+
+/* img (B,3,H,W) -> backbone features (B,112,H/16,W/16) before the neck
+ * (FEARNet.feature_extractor, fear_net.py:58-61). */
+int fear_backbone(FearContext* h, const float* d_img, int B, int H, int W, float* d_feat, void* stream);
+
+/* zfeat (Bz,256,8,8) with Bz == B or 1 (broadcast); xfeat (B,256,16,16)
+ * -> bbox (B,4,16,16) = exp(adjust*pred+bias), cls (B,1,16,16) = 0.1*pred (logits). */
+int fear_head(FearContext* h, const float* d_zfeat, int Bz, const float* d_xfeat, int B,
+              float* d_bbox, float* d_cls, void* stream);
+
+/* search (B,3,256,256) + zfeat (Bz,256,8,8) -> maps and (if non-null) decoded boxes[B].
+ * d_bbox / d_cls may be null when only boxes are wanted. */
+int fear_track(FearContext* h, const float* d_search, const float* d_zfeat, int Bz, int B,
+               float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);
+
+/* template (B,3,128,128) + search (B,3,256,256) -> maps (+ boxes). */
+int fear_forward(FearContext* h, const float* d_template, const float* d_search, int B,
+                 float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);
+
+/* Decode maps produced elsewhere: bbox (B,4,16,16), cls logits (B,1,16,16) -> boxes[B].
+ * apply_sigmoid = 0 treats cls as already-activated scores (decode(use_sigmoid=False)). */
+int fear_decode(const float* d_bbox, const float* d_cls, int B, int apply_sigmoid, FearBox* d_boxes,
+                void* stream);
+
+/* z (Bz,256,64), x (B,256,256)  [= (B,256,16,16)]  ->  out (B,320,256):
+ * out[:, :256] = x ; out[b, 256+k, p] = sum_c z[b,c,k] * x[b,c,p].   (blocks.py:121-124) */
+int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* stream);
+
+/* Channels-last core of the same contraction (the kernel the hot path launches):
+ * zt (Bz,64,256) [k][c], cat (B,256,320) [p][c'] whose first 256 channels hold x;
+ * writes cat[b, p, 256+k] = sum_c zt[b,k,c] * cat[b,p,c]. */
+int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream);
+
+/* ---- introspection (tests / bench) ---------------------------------------------------*/
+/* Select a kernel implementation for a stage by name, e.g. ("corr", "ffma" | "tcgen05").
+ * Returns FEAR_EINVAL for unknown names.  Default = best validated implementation. */
+int fear_set_option(FearContext* h, const char* key, const char* value);
+/* Number of kernels launched by this handle since creation (for bench's gpu_launches). */
+int64_t fear_launch_count(const FearContext* h);
+/* When enabled, every stage of the next calls is bracketed by CUDA events on `stream`;
+ * fear_stage_ms returns accumulated milliseconds and launch counts (synchronises events). */
+int fear_profile(FearContext* h, int enable);
+int fear_stage_count(void);
+const char* fear_stage_name(int i);
+int fear_stage_ms(FearContext* h, int i, float* ms, int64_t* launches);
+
+/* Debug: run the stem + the first `nblocks` backbone blocks (0..16) on img (B,3,H,W) and return
+ * that activation as NCHW; B must not exceed the reserved batch. */
+int fear_debug_backbone_prefix(FearContext* h, const float* d_img, int B, int H, int W, int nblocks,
+                               float* d_out, void* stream);
+/* Debug: copy a head intermediate of the last fear_head / fear_track / fear_forward call as NCHW
+ * (B,C,16,16): "search_features" | "cat_cls" | "cat_reg" (320 ch: encode output + correlation) |
+ * "cls_dw" | "reg_dw" | "x_reg" | "cls_tower" (256 ch).  (BoxTower.forward's 3rd/4th outputs.) */
+int fear_debug_head_tensor(FearContext* h, const char* name, int B, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEAR_B200_H */
