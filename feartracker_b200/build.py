@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libfear_b200.so")
 SOURCES = ["fear_context.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-lcuda",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 

@@ -1,0 +1,56 @@
+"""Stand-alone checker for the tcgen05 kernels (run in its own process: a device-side trap would
+poison the CUDA context of the main pytest process).  Prints one JSON object.
+
+    python tests/tc_check.py corr [B] [Bz]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from feartracker_b200 import _lib  # noqa: E402
+
+
+def corr_case(lib, B, Bz, impl, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    zt = torch.randn(Bz, 64, 256, generator=g)
+    cat = torch.randn(B, 256, 320, generator=g)
+    ref = torch.einsum("bpc,bkc->bpk", cat[:, :, :256].double(), (zt if Bz == B else zt.expand(B, 64, 256)).double())
+    _lib.check(lib.fear_set_option(None, b"corr", impl.encode()), "fear_set_option")
+    zc, cc = zt.cuda(), cat.cuda()
+    _lib.check(lib.fear_corr_nhwc_f32(zc.data_ptr(), Bz, cc.data_ptr(), B, torch.cuda.current_stream().cuda_stream),
+               "fear_corr_nhwc_f32")
+    torch.cuda.synchronize()
+    out = cc.cpu()
+    x_intact = bool(torch.equal(out[:, :, :256], cat[:, :, :256]))
+    got = out[:, :, 256:].double()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item()
+    # error map per (frame, 32-pixel block, 8-template-cell block) to localise layout mistakes
+    blocks = err.reshape(B, 8, 32, 8, 8).amax(dim=(2, 4)) / scale
+    return {
+        "impl": impl, "B": B, "Bz": Bz, "x_intact": x_intact, "max_err_rel": err.max().item() / scale,
+        "mean_err_rel": err.mean().item() / scale, "worst_block": blocks.flatten().argmax().item(),
+        "block_err_max_per_frame": blocks.amax(dim=(1, 2)).tolist(),
+        "sample_got": got[0, 0, :4].tolist(), "sample_ref": ref[0, 0, :4].tolist(),
+        "sample_got_p129": got[0, 129, :4].tolist(), "sample_ref_p129": ref[0, 129, :4].tolist(),
+    }
+
+
+def main():
+    mode = sys.argv[1]
+    lib = _lib.init(0)
+    res = {"mode": mode}
+    if mode == "corr":
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+        Bz = int(sys.argv[3]) if len(sys.argv) > 3 else B
+        res["ffma"] = corr_case(lib, B, Bz, "ffma")
+        res["tcgen05"] = corr_case(lib, B, Bz, "tcgen05")
+    print("TC_CHECK " + json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,13 +106,13 @@ def test_get_features_and_feature_extractor(net, sd64):
     assert zf.shape == (2, 256, 8, 8)
     zt4, _, _, _ = fo.synthetic_crops(4)
     zf4 = net.get_features(zt4.cuda()).cpu().numpy()
-    assert_maps_close(zf4, g["zf64"], "template features", tol=1e-4)
+    assert_maps_close(zf4, g["zf64"], "template features", inf_tol=1e-5)
     col = {}
     fo.get_features(sd64, xt.double(), col)
     fe = net.feature_extractor(xt.cuda())
     assert fe.shape == (2, 112, 16, 16)
-    assert_maps_close(fe.cpu().numpy(), col["xif4_7"].numpy(), "feature_extractor", tol=1e-4)
-    assert_maps_close(net.get_features(xt.cuda()).cpu().numpy(), col["neck"].numpy(), "search features", tol=1e-4)
+    assert_maps_close(fe.cpu().numpy(), col["xif4_7"].numpy(), "feature_extractor", inf_tol=1e-5)
+    assert_maps_close(net.get_features(xt.cuda()).cpu().numpy(), col["neck"].numpy(), "search features", inf_tol=1e-5)
 
 
 def test_head_intermediates(net, sd64):
@@ -133,7 +133,7 @@ def test_head_intermediates(net, sd64):
     assert all(v[1] < 1e-4 for v in report.values()), report
     bbox, cls, cls_dw, x_reg = net.connect_model(xf.float().cuda(), zf.float().cuda())
     assert torch.equal(bbox, out[R]) and cls_dw.shape == (2, 256, 16, 16)
-    assert_maps_close(x_reg.cpu().numpy(), col["x_reg"].numpy(), "x_reg", tol=1e-4)
+    assert_maps_close(x_reg.cpu().numpy(), col["x_reg"].numpy(), "x_reg", inf_tol=1e-5)
 
 
 def test_forward_seed0_golden(net):
@@ -195,7 +195,7 @@ def test_teacher_forced_video_frames(net):
     g = golden("video_teacher.npz")
     trk = fb.FEARTracker(net, cuda_id=0, **fb.FEAR_XS_TRACKER_KWARGS)
     zf = net.get_features(trk._preprocess_image(g["template_crop"]))
-    assert_maps_close(zf.cpu().numpy(), g["template_features"], "template features", tol=1e-4)
+    assert_maps_close(zf.cpu().numpy(), g["template_features"], "template features", inf_tol=1e-5)
     for i, crop in enumerate(g["search_crops"]):
         out = net.track(trk._preprocess_image(crop), zf)
         assert_maps_close(out[R].cpu().numpy(), g["reg64"][i:i + 1], f"reg frame {g['frames'][i]}")

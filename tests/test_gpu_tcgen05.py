@@ -1,0 +1,32 @@
+"""GPU: the tcgen05 (tensor-core, 3xTF32) kernels against an fp64 reference, each case in its own
+process so a device trap cannot poison the rest of the suite."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "gpurun_out")
+
+
+def _run(*args, timeout=180):
+    proc = subprocess.run([sys.executable, os.path.join(HERE, "tc_check.py"), *map(str, args)], capture_output=True,
+                          text=True, timeout=timeout)
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "tc_check_" + "_".join(map(str, args)) + ".log"), "w") as f:
+        f.write(proc.stdout + "\n--- stderr ---\n" + proc.stderr)
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("TC_CHECK ")]
+    assert proc.returncode == 0 and lines, f"tc_check {args} failed: {proc.stderr[-2000:]}"
+    return json.loads(lines[-1][len("TC_CHECK "):])
+
+
+@pytest.mark.parametrize("B,Bz", [(1, 1), (3, 3), (5, 1), (200, 200)])
+def test_corr_tcgen05(B, Bz):
+    res = _run("corr", B, Bz)
+    assert res["ffma"]["max_err_rel"] < 1e-5, res["ffma"]
+    tc = res["tcgen05"]
+    assert tc["x_intact"], "correlation kernel must not touch the x channels"
+    assert tc["max_err_rel"] < 1e-5, tc  # 3xTF32 keeps fp32-level accuracy
