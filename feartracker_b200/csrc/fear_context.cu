@@ -66,6 +66,8 @@ static Options g_default_options;
 
 struct PwW {
   const float* w = nullptr;  // [cout][cin]
+  const float* w_hi = nullptr;  // tf32 split of w for the tcgen05 path: w ~= w_hi + w_lo
+  const float* w_lo = nullptr;
   const float* b = nullptr;
   int cin = 0, cout = 0;
 };
@@ -177,7 +179,7 @@ static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, 
                      int ldr, float* C, int ldc, int M, int relu) {
   if (c->opt.pw == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
     LaunchScope scope(c, stage, s);
-    int r = tc::launch_pw(s, A, lda, w.w, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
+    int r = tc::launch_pw(s, A, lda, w.w_hi, w.w_lo, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
     if (r) return set_err(r, "tcgen05 pw launch failed (%d)", r);
     return check_launch("tc::pw");
   }
@@ -363,7 +365,15 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
 
   // Device arena: every tensor 256-byte aligned; depthwise [C][k][k] -> [k*k][C], stem -> [27][16].
   std::vector<float> arena;
-  std::vector<size_t> dev_off(n);
+  std::vector<size_t> dev_off(n), hi_off(n, 0), lo_off(n, 0);
+  auto is_gemm_weight = [&](const std::string& nm) {
+    if (nm.rfind("bbox_pred", 0) == 0 || nm.rfind("cls_pred", 0) == 0) return false;
+    auto ends = [&](const char* suf) {
+      const size_t l = strlen(suf);
+      return nm.size() >= l && nm.compare(nm.size() - l, l, suf) == 0;
+    };
+    return ends(".pw.w") || ends(".pwl.w") || nm == "neck.w";
+  };
   for (int i = 0; i < n; ++i) {
     size_t o = (arena.size() + 63) & ~(size_t)63;
     arena.resize(o + table[i].numel, 0.f);
@@ -388,6 +398,17 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
     } else {
       memcpy(&arena[o], src, sizeof(float) * table[i].numel);
     }
+    if (is_gemm_weight(nm)) {  // tf32 (hi, lo) split for the 3xTF32 tensor-core GEMM
+      for (int part = 0; part < 2; ++part) {
+        size_t po = (arena.size() + 63) & ~(size_t)63;
+        arena.resize(po + table[i].numel, 0.f);
+        (part == 0 ? hi_off : lo_off)[i] = po;
+        for (int64_t e = 0; e < table[i].numel; ++e) {
+          const float hi = tc::host_rna_tf32(src[e]);
+          arena[po + e] = part == 0 ? hi : tc::host_rna_tf32(src[e] - hi);
+        }
+      }
+    }
   }
   arena.resize((arena.size() + 63) & ~(size_t)63, 0.f);
 
@@ -407,50 +428,38 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
   }
   int idx = 0;
   auto next = [&]() { return (const float*)(c->d_weights + dev_off[idx++]); };
+  auto next_pw = [&](PwW& w, int cin, int cout) {  // weight (+ its hi/lo copies) followed by its bias
+    w.w_hi = c->d_weights + hi_off[idx];
+    w.w_lo = c->d_weights + lo_off[idx];
+    w.w = next();
+    w.b = next();
+    w.cin = cin;
+    w.cout = cout;
+  };
   c->stem_w = next();
   c->stem_b = next();
   for (int i = 0; i < kNumBlocks; ++i) {
     const IrfSpec& sp = kBlocks[i];
     BlockW& b = c->blocks[i];
-    if (sp.has_pw()) {
-      b.pw.w = next();
-      b.pw.b = next();
-      b.pw.cin = sp.cin;
-      b.pw.cout = sp.mid();
-    }
+    if (sp.has_pw()) next_pw(b.pw, sp.cin, sp.mid());
     b.dw.w = next();
     b.dw.b = next();
     b.dw.c = sp.mid();
     b.dw.k = sp.k;
-    b.pwl.w = next();
-    b.pwl.b = next();
-    b.pwl.cin = sp.mid();
-    b.pwl.cout = sp.cout;
+    next_pw(b.pwl, sp.mid(), sp.cout);
   }
-  c->neck.w = next();
-  c->neck.b = next();
-  c->neck.cin = kBackboneC;
-  c->neck.cout = kFeatC;
+  next_pw(c->neck, kBackboneC, kFeatC);
   for (int br = 0; br < 2; ++br) {
     BranchW& w = c->branch[br];
     w.enc_dw = {next(), nullptr, kFeatC, 3};
-    w.enc_pw.w = next();
-    w.enc_pw.b = next();
-    w.enc_pw.cin = kFeatC;
-    w.enc_pw.cout = kFeatC;
+    next_pw(w.enc_pw, kFeatC, kFeatC);
     w.corr_dw = {next(), nullptr, kCatC, 3};
-    w.corr_pw.w = next();
-    w.corr_pw.b = next();
-    w.corr_pw.cin = kCatC;
-    w.corr_pw.cout = kFeatC;
+    next_pw(w.corr_pw, kCatC, kFeatC);
   }
   for (int t = 0; t < 2; ++t)
     for (int i = 0; i < 2; ++i) {
       c->tower[t].dw[i] = {next(), nullptr, kFeatC, 3};
-      c->tower[t].pw[i].w = next();
-      c->tower[t].pw[i].b = next();
-      c->tower[t].pw[i].cin = kFeatC;
-      c->tower[t].pw[i].cout = kFeatC;
+      next_pw(c->tower[t].pw[i], kFeatC, kFeatC);
     }
   for (int t = 0; t < 2; ++t) {
     c->pred_dw[t] = {next(), nullptr, kFeatC, 3};

@@ -226,6 +226,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
+inline int init_pw();
 static int g_num_sms = 0;
 static bool g_tc_ready = false;
 
@@ -240,6 +241,7 @@ inline int init() {
     cudaGetLastError();
     return 0;
   }
+  if (init_pw()) return 0;
   g_tc_ready = true;
   return 0;
 }
@@ -259,10 +261,280 @@ inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int 
   return 0;
 }
 
-inline bool pw_supported(int, int) { return false; }
-inline int launch_pw(cudaStream_t, const float*, int, const float*, const float*, const float*, int, float*, int, int,
-                     int, int, int) {
-  return -1;
+// ------------------------------------------------------------------------------------------
+// pw_tc_kernel -- 1x1 convolution as a GEMM on tcgen05:  C[M][N] = act(A[M][K] * W[N][K]^T + bias (+ R))
+// A = channels-last activations (rows = pixels), W = BN-folded torch-native [Cout][Cin] weights,
+// pre-split on the host into tf32 (hi, lo) copies; A is split on the fly exactly like in the
+// correlation kernel.  Persistent CTAs walk (m_tile, n_tile) pairs, n fastest; tile = 128 pixels x NT
+// output channels (NT multiple of 16, <= 256), K streamed in 32-channel chunks through an S-stage ring
+// (S chosen from the stage size).  TMA zero-fills the K tail (Cin not a multiple of 32), rows >= M
+// and weight rows >= N.  Two TMEM accumulators of NT columns each overlap epilogue and MMA.
+// ------------------------------------------------------------------------------------------
+struct PwParams {
+  const float* bias;  // [N] or null
+  const float* R;     // residual [M][ldr] or null
+  float* C;
+  int ldr, ldc;
+  int M, N, NT, num_n_tiles, num_chunks, relu, stages, stage_bytes, tmem_cols;
+};
+
+constexpr int kPwThreads = 320;
+
+__global__ void __launch_bounds__(kPwThreads, 1)
+pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+             const __grid_constant__ CUtensorMap tmWl, const PwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* split = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* acc_full = bars + 3 * S;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m_tiles = (p.M + 127) >> 7;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+  const int w_bytes = p.NT * 128;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmWh);
+    prefetch_tmap(&tmWl);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 64) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto a_hi = [&](int s) { return smem + s * p.stage_bytes; };
+  auto a_lo = [&](int s) { return smem + s * p.stage_bytes + kCorrABytes; };
+  auto w_hi = [&](int s) { return smem + s * p.stage_bytes + 2 * kCorrABytes; };
+  auto w_lo = [&](int s) { return smem + s * p.stage_bytes + 2 * kCorrABytes + w_bytes; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kCorrABytes + 2 * w_bytes);
+          tma_load_2d(a_hi(stage), &tmA, &full[stage], c * 32, mt * 128);
+          tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
+          tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, p.NT);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * p.NT;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          mbar_wait(&split[stage], phase);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(stage));
+          const uint32_t bh = smem_u32(w_hi(stage)), bl = smem_u32(w_lo(stage));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
+            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
+            mma_tf32_ss(d, dal, dbh, idesc, 1);
+            mma_tf32_ss(d, dah, dbl, idesc, 1);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&acc_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    const int ts = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int c = 0; c < p.num_chunks; ++c) {
+        mbar_wait(&full[stage], phase);
+        float4* ah = reinterpret_cast<float4*>(a_hi(stage));
+        float4* al = reinterpret_cast<float4*>(a_lo(stage));
+#pragma unroll
+        for (int i = 0; i < kCorrABytes / 16 / 128; ++i) {
+          const float4 v = ah[ts + i * 128];
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          ah[ts + i * 128] = h;
+          al[ts + i * 128] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[stage]);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+      const int row = mt * 128 + q * 32 + lane;
+      const int n0 = nt * p.NT;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * p.NT + ((uint32_t)(q * 32) << 16);
+      const bool row_ok = row < p.M;
+      float* crow = p.C + (long long)row * p.ldc + n0;
+      const float* rrow = p.R ? p.R + (long long)row * p.ldr + n0 : nullptr;
+      for (int g = 0; g < p.NT; g += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr + g, r);  // warp-collective: executed by all lanes, valid row or not
+        tmem_ld_wait();
+        if (row_ok && n0 + g < p.N) {  // N is a multiple of 8; a 16-wide group may be half valid (N = 24)
+          const int valid = (p.N - (n0 + g)) >= 16 ? 16 : (p.N - (n0 + g));
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            if (v4 * 4 >= valid) break;
+            float4 o = make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]),
+                                   __uint_as_float(r[4 * v4 + 2]), __uint_as_float(r[4 * v4 + 3]));
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g) + v4);
+              o.x += b.x;
+              o.y += b.y;
+              o.z += b.z;
+              o.w += b.w;
+            }
+            if (rrow) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + g) + v4);
+              o.x += rr.x;
+              o.y += rr.y;
+              o.z += rr.z;
+              o.w += rr.w;
+            }
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            reinterpret_cast<float4*>(crow + g)[v4] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/driver slack
+
+// Output-channel tile for a layer: largest divisor-style tile <= 256 that is a multiple of 16.
+inline int pw_tile_n(int N) {
+  const int Np = (N + 15) & ~15;  // N = 24 -> 32 (weight rows >= N are zero-filled by TMA)
+  if (Np <= 256) return Np;
+  for (int parts = 2; parts <= 8; ++parts)
+    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 256) return Np / parts;
+  return 0;
+}
+
+inline bool pw_supported(int cin, int cout) {
+  return g_tc_ready && cin % 8 == 0 && cout % 8 == 0 && pw_tile_n(cout) != 0;
+}
+
+inline int init_pw() {
+  if (cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return 0;
+}
+
+// w_hi / w_lo: tf32-split copies of the [N][K] weights (device).
+inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi, const float* w_lo, const float* bias,
+                     const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu) {
+  if (!g_tc_ready) return -20;
+  PwParams p;
+  p.bias = bias;
+  p.R = R;
+  p.C = C;
+  p.ldr = ldr;
+  p.ldc = ldc;
+  p.M = M;
+  p.N = N;
+  p.NT = pw_tile_n(N);
+  if (!p.NT) return -21;
+  p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
+  p.num_chunks = (K + 31) / 32;
+  p.relu = relu;
+  p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
+  p.stages = (kPwMaxSmem - 1024 - 256) / p.stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  if (p.stages < 2) return -22;
+  int cols = 32;
+  while (cols < 2 * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap tmA, tmWh, tmWl;
+  int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmWh, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmWl, w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  const int tiles = ((M + 127) / 128) * p.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256;
+  pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
+  return 0;
 }
 
 }  // namespace tc

@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace fear {
 namespace tc {
@@ -174,6 +175,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+// 32 lanes x 16 consecutive columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // ---- UMMA descriptors --------------------------------------------------------------------
 // Shared-memory operand, K-major, 128-byte swizzle (rows of 128 B, 8-row atoms of 1024 B, tile base
 // 1024-B aligned): start address >> 4 in bits [0,14), LBO (unused for swizzled K-major) = 1 in
@@ -191,6 +203,16 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Host mirror of cvt.rna.tf32.f32 (round to nearest, ties away from zero; finite inputs).
+inline float host_rna_tf32(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
 }
 
 // fp32 -> (hi, lo) with hi = rna_tf32(v), lo = rna_tf32(v - hi): v ~= hi + lo to ~2^-22 relative.

@@ -40,6 +40,45 @@ def corr_case(lib, B, Bz, impl, seed=0):
     }
 
 
+def net_case(pw, corr):
+    """Whole network with the selected kernel implementations vs the fp64 oracle: per-block backbone
+    errors (localises a bad layer shape), head intermediates and the final maps."""
+    import feartracker_b200 as fb
+    from oracle import fear_oracle as fo
+    from tests.helpers import load_full_state, map_errors
+
+    sd = load_full_state()
+    net = fb.FEARNet(**fb.FEAR_XS_MODEL_KWARGS)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.reserve(4)
+    net.set_option("pw", pw)
+    net.set_option("corr", corr)
+    sd64 = fo.to_dtype({k: v for k, v in sd.items() if v.is_floating_point()}, torch.float64)
+    zt, xt, _, _ = fo.synthetic_crops(3)  # 3 frames: template branch M = 192 (M % 128 = 64 tail)
+    col = {}
+    zf64 = fo.get_features(sd64, zt.double())
+    xf64 = fo.get_features(sd64, xt.double(), col)
+    names = ["xif0_0"] + [s.name for s in fo.FBNET_C[1:fo.NUM_HOT_BLOCKS] if s.kind == "ir"]
+    res = {"pw": pw, "corr": corr, "blocks": {}}
+    for n, name in enumerate(names):
+        mine = net.backbone_prefix(xt.cuda(), n).cpu().numpy()
+        res["blocks"][name] = map_errors(mine, col[name].numpy())
+    zf = net.get_features(zt.cuda())
+    res["zf"] = map_errors(zf.cpu().numpy(), zf64.numpy())
+    hcol = {}
+    ref = fo.connector(sd64, zf64, xf64, hcol)
+    out = net.track(xt.cuda(), zf)
+    for name, want in (("cls_dw", hcol["cls_dw"]), ("reg_dw", hcol["reg_dw"]), ("x_reg", hcol["x_reg"]),
+                       ("cls_tower", hcol["cls_tower"])):
+        res[name] = map_errors(net.head_tensor(name, 3).cpu().numpy(), want.numpy())
+    for key, short in ((fo.TARGET_REGRESSION_LABEL_KEY, "reg"), (fo.TARGET_CLASSIFICATION_KEY, "cls")):
+        res[short] = map_errors(out[key].cpu().numpy(), ref[key].numpy())
+    res["argmax_same"] = bool((out[fo.TARGET_CLASSIFICATION_KEY].flatten(1).argmax(1).cpu()
+                               == ref[fo.TARGET_CLASSIFICATION_KEY].flatten(1).argmax(1)).all())
+    return res
+
+
 def main():
     mode = sys.argv[1]
     lib = _lib.init(0)
@@ -49,6 +88,8 @@ def main():
         Bz = int(sys.argv[3]) if len(sys.argv) > 3 else B
         res["ffma"] = corr_case(lib, B, Bz, "ffma")
         res["tcgen05"] = corr_case(lib, B, Bz, "tcgen05")
+    elif mode == "net":
+        res.update(net_case(sys.argv[2], sys.argv[3]))
     print("TC_CHECK " + json.dumps(res), flush=True)
 
 

@@ -30,3 +30,14 @@ def test_corr_tcgen05(B, Bz):
     tc = res["tcgen05"]
     assert tc["x_intact"], "correlation kernel must not touch the x channels"
     assert tc["max_err_rel"] < 1e-5, tc  # 3xTF32 keeps fp32-level accuracy
+
+
+@pytest.mark.parametrize("pw,corr", [("tcgen05", "ffma"), ("tcgen05", "tcgen05")])
+def test_network_with_tensor_core_kernels(pw, corr):
+    """Every 1x1 conv (all layer shapes of FEAR-XS) on the tcgen05 GEMM: block-by-block and final maps."""
+    res = _run("net", pw, corr, timeout=400)
+    bad = {k: v for k, v in res["blocks"].items() if v[1] > 1e-5}
+    assert not bad, bad
+    assert res["reg"][0] <= 1e-3 and res["reg"][1] <= 1e-3, res
+    assert res["cls"][0] <= 1e-3 and res["cls"][1] <= 1e-3, res
+    assert res["argmax_same"]
