@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--corr", default=None, help="correlation kernel implementation: ffma | tcgen05")
     ap.add_argument("--pw", default=None, help="1x1-conv implementation: ffma | tcgen05")
+    ap.add_argument("--dw", default=None, help="depthwise implementation: pixel | strip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -207,6 +208,8 @@ def main():
         _lib.check(_lib.load().fear_set_option(None, b"corr", args.corr.encode()), "fear_set_option")
     if args.pw:
         net.set_option("pw", args.pw)
+    if args.dw:
+        net.set_option("dw", args.dw)
 
     zt, xt = synthetic_batch(B, rank)
     x_host, z_dev = xt.pin_memory(), net.get_features(zt.to(dev))
@@ -309,7 +312,7 @@ def main():
                             "config 4 at 8 GPUs), FEAR-XS checkpoint weights",
                 "global_batch": total, "per_gpu_batch": B, "parallelism": f"frames sharded over {world} rank(s)",
                 "l2": "inputs larger than L2 (201 MB search batch per step; >2 GB of workspace traffic per step)",
-                "impl": {"corr": args.corr or "default", "pw": args.pw or "default"},
+                "impl": {"corr": args.corr or "default", "pw": args.pw or "default", "dw": args.dw or "default"},
             },
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + zf_host.numel() * 4),

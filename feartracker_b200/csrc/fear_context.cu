@@ -61,6 +61,7 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };
 struct Options {
   int corr = IMPL_FFMA;
   int pw = IMPL_FFMA;
+  int dw = 0;  // 0 = one pixel per thread, 1 = register-strip kernel
 };
 static Options g_default_options;
 
@@ -190,14 +191,35 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
                      int W, int stride, bool relu) {
   LaunchScope scope(c, stage, s);
   const int C4 = w.c / 4;
-  const long long total = (long long)B * (H / stride) * (W / stride) * C4;
   const int threads = 256;
-  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   const float4* i4 = reinterpret_cast<const float4*>(in);
   const float4* w4 = reinterpret_cast<const float4*>(w.w);
   const float4* b4 = reinterpret_cast<const float4*>(w.b);
   float4* o4 = reinterpret_cast<float4*>(out);
   const bool bias = w.b != nullptr;
+  const int Wo = W / stride;
+  if (c->opt.dw == 1 && Wo % 4 == 0) {
+    // register-strip kernels: 4 outputs per thread (stride 1) / 2 outputs per thread (stride 2)
+    const int TX = stride == 1 ? 4 : 2;
+    const long long total = (long long)B * (H / stride) * (Wo / TX) * C4;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    if (w.k == 3 && stride == 1 && relu && bias)
+      dw_conv_strip_kernel<3, 1, 4, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 3 && stride == 2 && relu && bias)
+      dw_conv_strip_kernel<3, 2, 2, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 5 && stride == 1 && relu && bias)
+      dw_conv_strip_kernel<5, 1, 4, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 5 && stride == 2 && relu && bias)
+      dw_conv_strip_kernel<5, 2, 2, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 3 && stride == 1 && !relu && !bias)
+      dw_conv_strip_kernel<3, 1, 4, false, false><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else
+      return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
+                     (int)bias);
+    return check_launch("dw_conv_strip_kernel");
+  }
+  const long long total = (long long)B * (H / stride) * Wo * C4;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   if (w.k == 3 && stride == 1 && relu && bias)
     dw_conv_nhwc_kernel<3, 1, true, true><<<blocks, threads, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
   else if (w.k == 3 && stride == 2 && relu && bias)
@@ -745,6 +767,12 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "dw")) {
+    if (!strcmp(value, "pixel")) o.dw = 0;
+    else if (!strcmp(value, "strip")) o.dw = 1;
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip)", value);
+    return 0;
+  }
   int impl;
   if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
   else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;

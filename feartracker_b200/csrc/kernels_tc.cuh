@@ -20,7 +20,8 @@
 //   warps 2-5   operand split: raw fp32 tile -> tf32 hi (in place) and lo (second tile), same swizzled
 //               positions, then fence.proxy.async so the tensor core sees the generic-proxy writes
 //   warps 6-9   epilogue: tcgen05.ld 128x64 fp32 accumulator -> registers -> global (256 B per pixel)
-// Two TMEM accumulators (2 x 64 columns) let the epilogue of tile t overlap the MMAs of tile t+1;
+// Two TMEM accumulator sets (2 x (64 main + 64 correction) columns) let the epilogue of tile t overlap
+// the MMAs of tile t+1;
 // a 4-stage smem ring (4 x 48 KB) keeps ~96 KB of loads in flight per SM.
 #pragma once
 #include <cuda_runtime.h>
@@ -37,7 +38,7 @@ constexpr int kCorrBBytes = 64 * 128;          // [64 template cells][32 ch] fp3
 constexpr int kCorrStageBytes = 2 * (kCorrABytes + kCorrBBytes);
 constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kCorrThreads = 320;
-constexpr int kCorrTmemCols = 128;
+constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) columns
 
 __global__ void __launch_bounds__(kCorrThreads, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -115,7 +116,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * 64;
+        const uint32_t d = tmem_base + acc * 128;  // main accumulator; +64 = correction accumulator
         for (int c = 0; c < 256 / kCorrChunk; ++c) {
           mbar_wait(&split[stage], phase);
           tc_fence_after();
@@ -125,9 +126,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 4; ++j) {  // 4 K-steps of 8 tf32 (32 B) inside the 128-B swizzle row
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
+            // so the (truncating) tensor-core adder rounds the big sum 3x less often
             mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d, dal, dbh, idesc, 1);
-            mma_tf32_ss(d, dah, dbl, idesc, 1);
+            mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
+            mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
           }
           tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
           if (++stage == kCorrStages) {
@@ -192,24 +195,27 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int frame = t >> 1, half = t & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 64 + ((uint32_t)(q * 32) << 16);
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(taddr, r0);
-      tmem_ld_32x32(taddr + 32, r1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);  // accumulator free for tile t+2
+      const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16);
       const long long row = (long long)frame * 256 + half * 128 + q * 32 + lane;
       float4* dst = reinterpret_cast<float4*>(cat + row * 320 + 256);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(__uint_as_float(r0[4 * i]), __uint_as_float(r0[4 * i + 1]), __uint_as_float(r0[4 * i + 2]),
-                             __uint_as_float(r0[4 * i + 3]));
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        uint32_t m[32], sm[32];
+        tmem_ld_32x32(taddr + hcol * 32, m);        // main (hi*hi)
+        tmem_ld_32x32(taddr + 64 + hcol * 32, sm);  // correction (lo*hi + hi*lo)
+        tmem_ld_wait();
+        if (hcol == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);  // accumulators free for tile t+2
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[8 + i] = make_float4(__uint_as_float(r1[4 * i]), __uint_as_float(r1[4 * i + 1]),
-                                 __uint_as_float(r1[4 * i + 2]), __uint_as_float(r1[4 * i + 3]));
+        for (int i = 0; i < 8; ++i)
+          dst[hcol * 8 + i] = make_float4(__uint_as_float(m[4 * i]) + __uint_as_float(sm[4 * i]),
+                                          __uint_as_float(m[4 * i + 1]) + __uint_as_float(sm[4 * i + 1]),
+                                          __uint_as_float(m[4 * i + 2]) + __uint_as_float(sm[4 * i + 2]),
+                                          __uint_as_float(m[4 * i + 3]) + __uint_as_float(sm[4 * i + 3]));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -357,7 +363,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * p.NT;
+        const uint32_t d = tmem_base + acc * 2 * p.NT;  // main; + NT = correction accumulator
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&split[stage], phase);
           tc_fence_after();
@@ -368,8 +374,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d, dal, dbh, idesc, 1);
-            mma_tf32_ss(d, dah, dbl, idesc, 1);
+            mma_tf32_ss(d + p.NT, dal, dbh, idesc, (c | j) != 0);
+            mma_tf32_ss(d + p.NT, dah, dbl, idesc, 1);
           }
           tc_commit(&empty[stage]);
           if (++stage == S) {
@@ -421,14 +427,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n0 = nt * p.NT;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * p.NT + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
       const bool row_ok = row < p.M;
       float* crow = p.C + (long long)row * p.ldc + n0;
       const float* rrow = p.R ? p.R + (long long)row * p.ldr + n0 : nullptr;
       for (int g = 0; g < p.NT; g += 16) {
-        uint32_t r[16];
+        uint32_t r[16], rs[16];
         tmem_ld_32x16(taddr + g, r);  // warp-collective: executed by all lanes, valid row or not
+        tmem_ld_32x16(taddr + p.NT + g, rs);
         tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rs[e]));
         if (row_ok && n0 + g < p.N) {  // N is a multiple of 8; a 16-wide group may be half valid (N = 24)
           const int valid = (p.N - (n0 + g)) >= 16 ? 16 : (p.N - (n0 + g));
 #pragma unroll
@@ -480,10 +489,11 @@ constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/d
 
 // Output-channel tile for a layer: largest divisor-style tile <= 256 that is a multiple of 16.
 inline int pw_tile_n(int N) {
+  // <= 128 so that 2 buffers x (main + correction) accumulators fit the 512 TMEM columns
   const int Np = (N + 15) & ~15;  // N = 24 -> 32 (weight rows >= N are zero-filled by TMA)
-  if (Np <= 256) return Np;
+  if (Np <= 128) return Np;
   for (int parts = 2; parts <= 8; ++parts)
-    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 256) return Np / parts;
+    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 128) return Np / parts;
   return 0;
 }
 
@@ -521,7 +531,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return -22;
   int cols = 32;
-  while (cols < 2 * p.NT) cols <<= 1;
+  while (cols < 4 * p.NT) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap tmA, tmWh, tmWl;
   int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);

@@ -227,3 +227,18 @@ def test_free_running_video_trajectory(net):
     # required identical up to the first such flip and the trajectories must stay locked together afterwards.
     assert same[:30].all(), f"early divergence at frame {first_diff + 1}"
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
+
+
+def test_depthwise_strip_kernel_is_bit_identical(net):
+    """The register-strip depthwise kernel accumulates in the same order as the per-pixel one."""
+    zt, xt, _, _ = fo.synthetic_crops(2)
+    zf = net.get_features(zt.cuda())
+    ref = net.track(xt.cuda(), zf)
+    net.set_option("dw", "strip")
+    try:
+        zf2 = net.get_features(zt.cuda())
+        out = net.track(xt.cuda(), zf2)
+    finally:
+        net.set_option("dw", "pixel")
+    assert torch.equal(zf, zf2)
+    assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
