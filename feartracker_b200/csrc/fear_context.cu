@@ -61,7 +61,7 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };
 struct Options {
   int corr = IMPL_FFMA;
   int pw = IMPL_FFMA;
-  int dw = 0;  // 0 = one pixel per thread, 1 = register-strip kernel
+  int dw = 0;  // 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
 };
 static Options g_default_options;
 
@@ -198,7 +198,28 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   float4* o4 = reinterpret_cast<float4*>(out);
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
-  if (c->opt.dw == 1 && Wo % 4 == 0) {
+  if (c->opt.dw == 2 && Wo % 4 == 0 && (H / stride) % 16 == 0) {
+    // rolling-window kernels: TX output columns x 16 output rows per thread, weights in registers
+    constexpr int ROWS = 16;
+    const int Ho = H / stride;
+#define ROLL_CASE(K_, S_, TX_, RELU_, BIAS_)                                                        \
+  {                                                                                                  \
+    const long long total = (long long)B * (Ho / ROWS) * (Wo / TX_) * C4;                            \
+    const unsigned blocks = (unsigned)((total + 127) / 128);                                         \
+    dw_conv_roll_kernel<K_, S_, TX_, ROWS, RELU_, BIAS_><<<blocks, 128, 0, s>>>(i4, w4, b4, o4, B, H, W, C4); \
+  }
+    if (w.k == 3 && stride == 1 && relu && bias) ROLL_CASE(3, 1, 4, true, true)
+    else if (w.k == 3 && stride == 2 && relu && bias) ROLL_CASE(3, 2, 4, true, true)
+    else if (w.k == 5 && stride == 1 && relu && bias) ROLL_CASE(5, 1, 2, true, true)
+    else if (w.k == 5 && stride == 2 && relu && bias) ROLL_CASE(5, 2, 2, true, true)
+    else if (w.k == 3 && stride == 1 && !relu && !bias) ROLL_CASE(3, 1, 4, false, false)
+    else
+      return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
+                     (int)bias);
+#undef ROLL_CASE
+    return check_launch("dw_conv_roll_kernel");
+  }
+  if (c->opt.dw >= 1 && Wo % 4 == 0) {
     // register-strip kernels: 4 outputs per thread (stride 1) / 2 outputs per thread (stride 2)
     const int TX = stride == 1 ? 4 : 2;
     const long long total = (long long)B * (H / stride) * (Wo / TX) * C4;
@@ -245,16 +266,22 @@ static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int
 }
 
 // cat[b, p, 256 + k] = sum_c zt[b, k, c] * cat[b, p, c]    (MobileCorrelation matmul, blocks.py:123)
-static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B) {
+// `groups` consecutive [B][256][320] buffers starting at cat share the templates (head: cls + reg branch).
+static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B,
+                       int groups) {
   if (opt.corr == IMPL_TC) {
     LaunchScope scope(c, ST_CORR, s);
-    int r = tc::launch_corr(s, zt, Bz, cat, B);
+    int r = tc::launch_corr(s, zt, Bz, cat, B, groups);
     if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
     return check_launch("tc::corr");
   }
-  return launch_gemm_ffma(c, ST_CORR, s, cat, kCatC, (long long)kScorePix * kCatC, zt, kFeatC,
-                          Bz == 1 ? 0 : (long long)kCorrC * kFeatC, nullptr, nullptr, 0, cat + kFeatC, kCatC,
-                          (long long)kScorePix * kCatC, kScorePix, kCorrC, kFeatC, 0, B);
+  for (int g = 0; g < groups; ++g) {
+    float* cg = cat + (long long)g * B * kScorePix * kCatC;
+    FEAR_TRY(launch_gemm_ffma(c, ST_CORR, s, cg, kCatC, (long long)kScorePix * kCatC, zt, kFeatC,
+                              Bz == 1 ? 0 : (long long)kCorrC * kFeatC, nullptr, nullptr, 0, cg + kFeatC, kCatC,
+                              (long long)kScorePix * kCatC, kScorePix, kCorrC, kFeatC, 0, B));
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------ executor
@@ -302,13 +329,18 @@ static int run_features(FearContext* c, cudaStream_t s, const float* img, int B,
 static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, const float* F, int B, float* bbox,
                     float* cls) {
   const int M = B * kScorePix;
+  // the two concat buffers are laid out back to back for THIS batch so one correlation launch covers both
+  c->hCAT[1] = c->hCAT[0] + (long long)B * kScorePix * kCatC;
   for (int br = 0; br < 2; ++br) {
     const BranchW& w = c->branch[br];
     // MatrixMobile: x -> dw3x3 -> 1x1 (+BN) -> ReLU, written into channels [0,256) of the concat buffer
     FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, F, w.enc_dw, c->hT, B, kScore, kScore, 1, false));
     FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, w.enc_pw, nullptr, 0, c->hCAT[br], kCatC, M, 1));
-    // pixel-wise correlation into channels [256,320)
-    FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[br], B));
+  }
+  // pixel-wise correlation of both branches into channels [256,320) of their concat buffers
+  FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2));
+  for (int br = 0; br < 2; ++br) {
+    const BranchW& w = c->branch[br];
     // MobileCorrelation.enc: dw3x3(320) -> 1x1 320->256 (+BN) -> ReLU
     FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, c->hCAT[br], w.corr_dw, c->hT, B, kScore, kScore, 1, false));
     FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kCatC, w.corr_pw, nullptr, 0, c->hD[br], kFeatC, M, 1));
@@ -676,7 +708,7 @@ extern "C" int fear_decode(const float* d_bbox, const float* d_cls, int B, int a
 extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream) {
   if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
-  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B);
+  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B, 1);
 }
 
 // Scratch for the handle-less NCHW wrapper; grows (cudaMalloc) only when a larger batch arrives.
@@ -703,7 +735,7 @@ extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, 
                             kFeatC, kCorrC, Bz));
   FEAR_TRY(launch_transpose(nullptr, s, d_x, kScorePix, (long long)kFeatC * kScorePix, cat, kCatC,
                             (long long)kScorePix * kCatC, kFeatC, kScorePix, B));
-  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B));
+  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B, 1));
   // cat [p][320] -> out [320][p]
   return launch_transpose(nullptr, s, cat, kCatC, (long long)kScorePix * kCatC, d_out, kScorePix,
                           (long long)kCatC * kScorePix, kScorePix, kCatC, B);
@@ -770,7 +802,8 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   if (!strcmp(key, "dw")) {
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip)", value);
+    else if (!strcmp(value, "roll")) o.dw = 2;
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll)", value);
     return 0;
   }
   int impl;

@@ -176,6 +176,103 @@ __global__ void __launch_bounds__(256) dw_conv_strip_kernel(const float4* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// Depthwise KxK conv, rolling-window version.  One thread owns (4 channels, TX output columns) and
+// walks ROWS output rows top to bottom: all K*K weights live in registers, every input row segment
+// is loaded ONCE and scattered into a ring of ceil(K/S) live output-row accumulators, so a 5x5 conv
+// issues ~3 loads per output float4 instead of ~16 (strip) / 50 (per-pixel).  That moves the kernel
+// from L1-wavefront-bound to FFMA/HBM-bound.  Fully unrolled => all ring indices are compile time.
+// Accumulation order per output (bias, then ky, kx ascending) is identical to the other two kernels.
+// ------------------------------------------------------------------------------------------
+template <int K, int S, int TX, int ROWS, bool RELU, bool BIAS>
+__global__ void __launch_bounds__(128) dw_conv_roll_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
+                                                           const float4* __restrict__ bias, float4* __restrict__ out,
+                                                           int B, int H, int W, int C4) {
+  constexpr int P = K / 2;
+  constexpr int NIN = (TX - 1) * S + K;
+  constexpr int LIVE = (K + S - 1) / S;
+  constexpr int NR = (ROWS - 1) * S + K;  // input rows feeding ROWS output rows
+  const int Ho = H / S, Wo = W / S;
+  const int strips = Wo / TX, segs = (Ho + ROWS - 1) / ROWS;
+  const long long total = (long long)B * segs * strips * C4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long rest = idx / C4;
+  const int sx = (int)(rest % strips);
+  rest /= strips;
+  const int seg = (int)(rest % segs);
+  const int b = (int)(rest / segs);
+  const int oy0 = seg * ROWS, ox0 = sx * TX;
+  const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
+
+  float4 wr[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) wr[i] = __ldg(w + i * C4 + c4);
+  const float4 b4 = BIAS ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[LIVE][TX];
+#pragma unroll
+  for (int l = 0; l < LIVE; ++l)
+#pragma unroll
+    for (int t = 0; t < TX; ++t) acc[l][t] = b4;
+
+  const float4* inb = in + (long long)b * H * W * C4 + c4;
+  float4* outb = out + (long long)b * Ho * Wo * C4 + c4;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int iy = iy0 + r;
+    if (iy >= 0 && iy < H) {
+      const float4* row = inb + (long long)iy * W * C4;
+      float4 v[NIN];
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) {
+        const int ix = ix0 + i;
+        v[i] = (ix >= 0 && ix < W) ? __ldg(row + (long long)ix * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int ky = K - 1; ky >= 0; --ky) {  // descending ky = ascending output row; order per output unchanged
+        if ((r - ky) >= 0 && (r - ky) % S == 0 && (r - ky) / S < ROWS) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int slot = ((r - ky) / S) % LIVE;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float4 k = wr[ky * K + kx];
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+              const float4 x = v[t * S + kx];
+              acc[slot][t].x = fmaf(x.x, k.x, acc[slot][t].x);
+              acc[slot][t].y = fmaf(x.y, k.y, acc[slot][t].y);
+              acc[slot][t].z = fmaf(x.z, k.z, acc[slot][t].z);
+              acc[slot][t].w = fmaf(x.w, k.w, acc[slot][t].w);
+            }
+          }
+        }
+      }
+    }
+    if (r >= K - 1 && (r - (K - 1)) % S == 0) {  // output row o is complete after input row r
+      const int o = (r - (K - 1)) / S;
+      const int slot = o % LIVE;
+      if (oy0 + o < Ho) {
+        float4* orow = outb + ((long long)(oy0 + o) * Wo + ox0) * C4;
+#pragma unroll
+        for (int t = 0; t < TX; ++t) {
+          float4 res = acc[slot][t];
+          if (RELU) {
+            res.x = fmaxf(res.x, 0.f);
+            res.y = fmaxf(res.y, 0.f);
+            res.z = fmaxf(res.z, 0.f);
+            res.w = fmaxf(res.w, 0.f);
+          }
+          orow[(long long)t * C4] = res;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < TX; ++t) acc[slot][t] = b4;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 1x1 conv / correlation as a GEMM on CUDA cores:  C[M][N] = A[M][K] * Bw[N][K]^T (+bias)(+R)(ReLU)
 // A rows = pixels (lda floats apart), Bw rows = output channels (ldb apart), both K-contiguous.
 // Tile 128 x BN x 16, 256 threads as 32 (rows, 4 each) x 8 (cols, TN = BN/8 each).

@@ -36,13 +36,13 @@ constexpr int kCorrChunk = 32;                 // channels per stage = one 128-b
 constexpr int kCorrABytes = 128 * 128;         // [128 pixels][32 ch] fp32
 constexpr int kCorrBBytes = 64 * 128;          // [64 template cells][32 ch] fp32
 constexpr int kCorrStageBytes = 2 * (kCorrABytes + kCorrBBytes);
-constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
 constexpr int kCorrThreads = 320;
 constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) columns
 
 __global__ void __launch_bounds__(kCorrThreads, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               float* __restrict__ cat, int num_frames, int z_broadcast) {
+               float* __restrict__ cat, int num_frames, int z_mod) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes);
@@ -52,6 +52,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 3 * kCorrStages; // [2] accumulator complete
   uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = num_frames * 2;
@@ -94,7 +95,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int frame = t >> 1, half = t & 1;
         const int arow = frame * 256 + half * 128;
-        const int brow = z_broadcast ? 0 : frame * 64;
+        const int brow = z_mod ? (frame % z_mod) * 64 : 0;  // z_mod = 0: one template for every frame
         for (int c = 0; c < 256 / kCorrChunk; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], kCorrABytes + kCorrBBytes);
@@ -196,25 +197,35 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16);
-      const long long row = (long long)frame * 256 + half * 128 + q * 32 + lane;
-      float4* dst = reinterpret_cast<float4*>(cat + row * 320 + 256);
+      const long long row0 = (long long)frame * 256 + half * 128 + q * 32;
+      float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
 #pragma unroll
-      for (int hcol = 0; hcol < 2; ++hcol) {
-        uint32_t m[32], sm[32];
-        tmem_ld_32x32(taddr + hcol * 32, m);        // main (hi*hi)
-        tmem_ld_32x32(taddr + 64 + hcol * 32, sm);  // correction (lo*hi + hi*lo)
+      for (int g = 0; g < 64; g += 16) {
+        uint32_t m[16], sm[16];
+        tmem_ld_32x16(taddr + g, m);        // main (hi*hi)
+        tmem_ld_32x16(taddr + 64 + g, sm);  // correction (lo*hi + hi*lo)
         tmem_ld_wait();
-        if (hcol == 1) {
+        if (g == 48) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);  // accumulators free for tile t+2
         }
+        // per-warp 32 x 16 transpose through smem so each store instruction writes 8 rows x 64 B
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[hcol * 8 + i] = make_float4(__uint_as_float(m[4 * i]) + __uint_as_float(sm[4 * i]),
-                                          __uint_as_float(m[4 * i + 1]) + __uint_as_float(sm[4 * i + 1]),
-                                          __uint_as_float(m[4 * i + 2]) + __uint_as_float(sm[4 * i + 2]),
-                                          __uint_as_float(m[4 * i + 3]) + __uint_as_float(sm[4 * i + 3]));
+        for (int j = 0; j < 4; ++j)
+          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+              make_float4(__uint_as_float(m[4 * j]) + __uint_as_float(sm[4 * j]),
+                          __uint_as_float(m[4 * j + 1]) + __uint_as_float(sm[4 * j + 1]),
+                          __uint_as_float(m[4 * j + 2]) + __uint_as_float(sm[4 * j + 2]),
+                          __uint_as_float(m[4 * j + 3]) + __uint_as_float(sm[4 * j + 3]));
+        __syncwarp();
+        const int j = lane & 3;
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          const int rl = rb * 8 + (lane >> 2);
+          *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
+        }
+        __syncwarp();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -254,16 +265,20 @@ inline int init() {
 
 inline bool available() { return g_tc_ready; }
 
-inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int B) {
+// cat holds `groups` consecutive [B][256][320] buffers (the cls and reg branches of the head): frame f of
+// every group correlates with template f (or template 0 when Bz == 1).  One launch for all groups keeps
+// the persistent grid busy for ~7 tile rounds instead of 3.46, i.e. almost no tail.
+inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int B, int groups) {
   if (!g_tc_ready) return -20;
   CUtensorMap tmA, tmB;
-  int r = make_tmap_2d(&tmA, cat, (uint64_t)B * 256, 320, 320, 128, kCorrChunk);
+  const int frames = B * groups;
+  int r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
   if (r) return r;
   r = make_tmap_2d(&tmB, zt, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
   if (r) return r;
-  const int tiles = B * 2;
+  const int tiles = frames * 2;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  corr_tc_kernel<<<grid, kCorrThreads, kCorrSmemBytes, s>>>(tmA, tmB, cat, B, Bz == 1 ? 1 : 0);
+  corr_tc_kernel<<<grid, kCorrThreads, kCorrSmemBytes, s>>>(tmA, tmB, cat, frames, Bz == 1 ? 0 : B);
   return 0;
 }
 
@@ -299,6 +314,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_full = bars + 3 * S;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_tiles = (p.M + 127) >> 7;
@@ -423,51 +439,59 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
-      const int row = mt * 128 + q * 32 + lane;
       const int n0 = nt * p.NT;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
-      const bool row_ok = row < p.M;
-      float* crow = p.C + (long long)row * p.ldc + n0;
-      const float* rrow = p.R ? p.R + (long long)row * p.ldr + n0 : nullptr;
+      // Per-warp 32 x 16 staging tile (2 KB, XOR-swizzled 16-byte chunks): the accumulator arrives one
+      // row per lane; it leaves as 8 rows x 64 contiguous bytes per store instruction (full sectors).
+      float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
       for (int g = 0; g < p.NT; g += 16) {
         uint32_t r[16], rs[16];
-        tmem_ld_32x16(taddr + g, r);  // warp-collective: executed by all lanes, valid row or not
+        tmem_ld_32x16(taddr + g, r);
         tmem_ld_32x16(taddr + p.NT + g, rs);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(rs[e]));
-        if (row_ok && n0 + g < p.N) {  // N is a multiple of 8; a 16-wide group may be half valid (N = 24)
-          const int valid = (p.N - (n0 + g)) >= 16 ? 16 : (p.N - (n0 + g));
+        for (int j = 0; j < 4; ++j)
+          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+              make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]),
+                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]));
+        __syncwarp();
+        const int j = lane & 3;
+        const int col = n0 + g + j * 4;
+        if (col < p.N) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            if (v4 * 4 >= valid) break;
-            float4 o = make_float4(__uint_as_float(r[4 * v4]), __uint_as_float(r[4 * v4 + 1]),
-                                   __uint_as_float(r[4 * v4 + 2]), __uint_as_float(r[4 * v4 + 3]));
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g) + v4);
+          for (int rb = 0; rb < 4; ++rb) {
+            const int rl = rb * 8 + (lane >> 2);
+            const long long grow = (long long)mt * 128 + q * 32 + rl;
+            if (grow < p.M) {
+              float4 o = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
               o.x += b.x;
               o.y += b.y;
               o.z += b.z;
               o.w += b.w;
+              if (p.R) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.R + grow * p.ldr + col));
+                o.x += rr.x;
+                o.y += rr.y;
+                o.z += rr.z;
+                o.w += rr.w;
+              }
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = o;
             }
-            if (rrow) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + g) + v4);
-              o.x += rr.x;
-              o.y += rr.y;
-              o.z += rr.z;
-              o.w += rr.w;
-            }
-            if (p.relu) {
-              o.x = fmaxf(o.x, 0.f);
-              o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f);
-              o.w = fmaxf(o.w, 0.f);
-            }
-            reinterpret_cast<float4*>(crow + g)[v4] = o;
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -527,7 +551,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.num_chunks = (K + 31) / 32;
   p.relu = relu;
   p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
-  p.stages = (kPwMaxSmem - 1024 - 256) / p.stage_bytes;
+  p.stages = (kPwMaxSmem - 1024 - 256 - 8192) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return -22;
   int cols = 32;
@@ -542,7 +566,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   if (r) return r;
   const int tiles = ((M + 127) / 128) * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256 + 8192;
   pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
   return 0;
 }

@@ -229,12 +229,14 @@ def test_free_running_video_trajectory(net):
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
 
 
-def test_depthwise_strip_kernel_is_bit_identical(net):
-    """The register-strip depthwise kernel accumulates in the same order as the per-pixel one."""
+@pytest.mark.parametrize("impl", ["strip", "roll"])
+def test_depthwise_variants_are_bit_identical(net, impl):
+    """The register-strip / rolling-window depthwise kernels accumulate in the same order as the per-pixel one."""
     zt, xt, _, _ = fo.synthetic_crops(2)
+    net.set_option("dw", "pixel")
     zf = net.get_features(zt.cuda())
     ref = net.track(xt.cuda(), zf)
-    net.set_option("dw", "strip")
+    net.set_option("dw", impl)
     try:
         zf2 = net.get_features(zt.cuda())
         out = net.track(xt.cuda(), zf2)
