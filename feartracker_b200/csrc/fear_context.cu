@@ -56,7 +56,7 @@ enum Stage {
 static const char* kStageNames[ST_COUNT] = {"stem",    "backbone_pw", "backbone_dw", "neck",   "head_dw",
                                             "head_pw", "corr",        "pred",        "decode", "layout"};
 
-enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };
+enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 A-from-smem | tcgen05 A-from-TMEM
 
 struct Options {
   int corr = IMPL_FFMA;
@@ -115,6 +115,7 @@ struct FearContext {
   float *hF = nullptr, *hT = nullptr, *hCAT[2] = {nullptr, nullptr}, *hD[2] = {nullptr, nullptr}, *hP = nullptr;
   float* hQ[2] = {nullptr, nullptr};  // tower outputs: [0] = bbox tower (x_reg), [1] = cls tower
   float *zt = nullptr, *mapB = nullptr, *mapC = nullptr;
+  float *zth = nullptr, *ztl = nullptr;  // tf32 (hi, lo) split of zt for the TS correlation
 
   int64_t launches = 0;
   bool profiling = false;
@@ -178,6 +179,13 @@ static int launch_gemm_ffma(FearContext* c, int stage, cudaStream_t s, const flo
 // 1x1 conv over M pixels: out = act(A * W^T + b (+R)).
 static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, int lda, const PwW& w, const float* R,
                      int ldr, float* C, int ldc, int M, int relu) {
+  if (c->opt.pw == IMPL_TS && tc::pw_supported(w.cin, w.cout) && tc::ts_tile_n(w.cout)) {
+    LaunchScope scope(c, stage, s);
+    int r = tc::launch_gemm_ts(s, A, lda, w.w_hi, w.w_lo, (uint64_t)w.cout, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu,
+                               0, 1, 0);
+    if (r) return set_err(r, "tcgen05 (TS) pw launch failed (%d)", r);
+    return check_launch("tc::gemm_ts");
+  }
   if (c->opt.pw == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
     LaunchScope scope(c, stage, s);
     int r = tc::launch_pw(s, A, lda, w.w_hi, w.w_lo, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
@@ -198,7 +206,8 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   float4* o4 = reinterpret_cast<float4*>(out);
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
-  if (c->opt.dw == 2 && Wo % 4 == 0 && (H / stride) % 16 == 0) {
+  const bool want_roll = c->opt.dw == 2 || (c->opt.dw == 3 && w.k == 3 && stride == 1);
+  if (want_roll && Wo % 4 == 0 && (H / stride) % 16 == 0) {
     // rolling-window kernels: TX output columns x 16 output rows per thread, weights in registers
     constexpr int ROWS = 16;
     const int Ho = H / stride;
@@ -268,8 +277,22 @@ static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int
 // cat[b, p, 256 + k] = sum_c zt[b, k, c] * cat[b, p, c]    (MobileCorrelation matmul, blocks.py:123)
 // `groups` consecutive [B][256][320] buffers starting at cat share the templates (head: cls + reg branch).
 static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B,
-                       int groups) {
-  if (opt.corr == IMPL_TC) {
+                       int groups, float* zth = nullptr, float* ztl = nullptr) {
+  if (opt.corr == IMPL_TS && zth && ztl) {
+    {
+      LaunchScope scope(c, ST_LAYOUT, s);  // template features -> tf32 (hi, lo) planes
+      const long long n4 = (long long)Bz * kCorrC * kFeatC / 4;
+      tc::split_hi_lo_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
+          reinterpret_cast<const float4*>(zt), reinterpret_cast<float4*>(zth), reinterpret_cast<float4*>(ztl), n4);
+      FEAR_TRY(check_launch("split_hi_lo_kernel"));
+    }
+    LaunchScope scope(c, ST_CORR, s);
+    int r = tc::launch_gemm_ts(s, cat, kCatC, zth, ztl, (uint64_t)Bz * kCorrC, nullptr, nullptr, 0, cat + kFeatC, kCatC,
+                               B * groups * kScorePix, kCorrC, kFeatC, 0, 2, Bz == 1 ? 1 : B, kCorrC);
+    if (r) return set_err(r, "tcgen05 (TS) corr launch failed (%d)", r);
+    return check_launch("tc::gemm_ts(corr)");
+  }
+  if (opt.corr == IMPL_TC || opt.corr == IMPL_TS) {
     LaunchScope scope(c, ST_CORR, s);
     int r = tc::launch_corr(s, zt, Bz, cat, B, groups);
     if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
@@ -338,7 +361,7 @@ static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, con
     FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, w.enc_pw, nullptr, 0, c->hCAT[br], kCatC, M, 1));
   }
   // pixel-wise correlation of both branches into channels [256,320) of their concat buffers
-  FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2));
+  FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2, c->zth, c->ztl));
   for (int br = 0; br < 2; ++br) {
     const BranchW& w = c->branch[br];
     // MobileCorrelation.enc: dw3x3(320) -> 1x1 320->256 (+BN) -> ReLU
@@ -552,6 +575,7 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
       (int64_t)kScorePix * kFeatC, (int64_t)kScorePix * kFeatC,     // hQ[2]
       (int64_t)kTmplPix * kFeatC,                                   // zt
       4 * kScorePix, kScorePix,                                     // mapB mapC
+      (int64_t)kTmplPix * kFeatC, (int64_t)kTmplPix * kFeatC,       // zth ztl
   };
   int64_t total = 0;
   std::vector<int64_t> offs;
@@ -580,6 +604,8 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
   c->zt = p + offs[13];
   c->mapB = p + offs[14];
   c->mapC = p + offs[15];
+  c->zth = p + offs[16];
+  c->ztl = p + offs[17];
   c->reserved = max_batch;
   return 0;
 }
@@ -705,10 +731,31 @@ extern "C" int fear_decode(const float* d_bbox, const float* d_cls, int B, int a
   return run_decode(nullptr, (cudaStream_t)stream, d_bbox, d_cls, B, apply_sigmoid, d_boxes);
 }
 
+// second scratch (hi/lo template planes of the handle-less channels-last correlation)
+static float* g_scratch2 = nullptr;
+static size_t g_scratch2_floats = 0;
+static int ensure_scratch2(size_t need) {
+  if (need <= g_scratch2_floats) return 0;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (g_scratch2) cudaFree(g_scratch2);
+  g_scratch2 = nullptr;
+  g_scratch2_floats = 0;
+  CUDA_TRY(cudaMalloc(&g_scratch2, need * sizeof(float)));
+  g_scratch2_floats = need;
+  return 0;
+}
+
 extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream) {
   if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
-  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B, 1);
+  float *zth = nullptr, *ztl = nullptr;
+  if (g_default_options.corr == IMPL_TS) {
+    const size_t need = 2 * (size_t)Bz * kCorrC * kFeatC;
+    FEAR_TRY(ensure_scratch2(need));
+    zth = g_scratch2;
+    ztl = g_scratch2 + (size_t)Bz * kCorrC * kFeatC;
+  }
+  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B, 1, zth, ztl);
 }
 
 // Scratch for the handle-less NCHW wrapper; grows (cudaMalloc) only when a larger batch arrives.
@@ -719,7 +766,7 @@ extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, 
   if (!d_z || !d_x || !d_out || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t need = (size_t)B * kScorePix * kCatC + (size_t)Bz * kCorrC * kFeatC;
+  const size_t need = (size_t)B * kScorePix * kCatC + 3 * (size_t)Bz * kCorrC * kFeatC;
   if (need > g_scratch_floats) {
     CUDA_TRY(cudaDeviceSynchronize());
     if (g_scratch) cudaFree(g_scratch);
@@ -735,7 +782,8 @@ extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, 
                             kFeatC, kCorrC, Bz));
   FEAR_TRY(launch_transpose(nullptr, s, d_x, kScorePix, (long long)kFeatC * kScorePix, cat, kCatC,
                             (long long)kScorePix * kCatC, kFeatC, kScorePix, B));
-  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B, 1));
+  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B, 1, zt + (size_t)Bz * kCorrC * kFeatC,
+                       zt + 2 * (size_t)Bz * kCorrC * kFeatC));
   // cat [p][320] -> out [320][p]
   return launch_transpose(nullptr, s, cat, kCatC, (long long)kScorePix * kCatC, d_out, kScorePix,
                           (long long)kCatC * kScorePix, kScorePix, kCatC, B);
@@ -803,14 +851,16 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
     else if (!strcmp(value, "roll")) o.dw = 2;
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll)", value);
+    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, strip otherwise
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | auto)", value);
     return 0;
   }
   int impl;
   if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
   else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;
-  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (ffma | tcgen05)", value);
-  if (impl == IMPL_TC && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
+  else if (!strcmp(value, "tcgen05ts")) impl = IMPL_TS;
+  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (ffma | tcgen05 | tcgen05ts)", value);
+  if (impl != IMPL_FFMA && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
   if (!strcmp(key, "corr")) o.corr = impl;
   else if (!strcmp(key, "pw")) o.pw = impl;
   else return set_err(FEAR_EINVAL, "unknown option '%s' (corr | pw)", key);

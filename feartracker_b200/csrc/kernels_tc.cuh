@@ -511,6 +511,343 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/driver slack
 
+// ------------------------------------------------------------------------------------------
+// gemm_ts_kernel -- second-generation tensor-core GEMM: the activation operand lives in TENSOR MEMORY.
+//
+// Profiling the SS kernels above (profiles/r1_*) showed them bound by shared-memory bandwidth, not by
+// HBM or the tensor pipe: per 32-channel chunk the smem port moved TMA writes + split reads/writes
+// (hi rewritten in place, lo tile written) + three MMAs each re-reading the A tile (~170-190 KB/chunk).
+// Here the convert warps read the raw fp32 A tile from smem ONCE, split it in registers and park
+// (hi, lo) in TMEM with tcgen05.st; the MMAs take A from TMEM ("TS" form) and only the B operand from
+// smem.  A's smem slot is free as soon as it has been read, so the A ring and the B ring have
+// independent depths and more bytes stay in flight.
+//
+//   C[M][ldc] = act(A[M][K] * Bm[g][N][K]^T + bias (+R)),   Bm pre-split into tf32 (hi, lo) planes.
+//   Tile = 128 rows x NT cols.  Group g of a tile selects the B matrix: g = (mt / tiles_per_group) %
+//   group_mod  (1x1 conv: one shared B; correlation: one template per frame, 2 row tiles per frame).
+//
+// TMEM columns: [0,128) two A slots (32 hi + 32 lo each); then `sets` x (main NT | correction NT).
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 convert, warps 6-9 epilogue.
+// ------------------------------------------------------------------------------------------
+struct TsParams {
+  const float* bias;
+  const float* R;
+  float* C;
+  int ldr, ldc;
+  int M, N, NT, num_n_tiles, num_chunks, relu;
+  int a_slots, w_slots, w_slot_bytes, acc_sets, tmem_cols;
+  int tiles_per_group, group_mod, group_rows;  // B-matrix selection (0 tiles_per_group = single shared B)
+};
+
+constexpr int kTsThreads = 320;
+constexpr int kTsASlotBytes = 128 * 128;
+
+__global__ void __launch_bounds__(kTsThreads, 1)
+gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+               const __grid_constant__ CUtensorMap tmWl, const TsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + p.a_slots * kTsASlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + p.w_slots * p.w_slot_bytes);
+  uint64_t* a_full = bars;                 // [8] TMA landed A
+  uint64_t* a_empty = bars + 8;            // [8] convert warps have read the slot (count 4)
+  uint64_t* w_full = bars + 16;            // [8] TMA landed W hi + lo
+  uint64_t* w_empty = bars + 24;           // [8] MMAs that read the slot completed (commit)
+  uint64_t* ta_full = bars + 32;           // [2] (hi, lo) written to the TMEM A slot (count 4)
+  uint64_t* ta_empty = bars + 34;          // [2] MMAs that read the TMEM A slot completed (commit)
+  uint64_t* acc_full = bars + 36;          // [2]
+  uint64_t* acc_empty = bars + 38;         // [2] (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 512;  // 4 warps x 2 KB
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m_tiles = (p.M + 127) >> 7;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+  const int w_half = p.NT * 128;  // bytes of one [NT][32] fp32 tile
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmWh);
+    prefetch_tmap(&tmWl);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 64) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 4);
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ta_full[a], 4);
+      mbar_init(&ta_empty[a], 1);
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_col0 = 128;  // accumulators start after the two A slots
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+        int wrow = nt * p.NT;
+        if (p.tiles_per_group) wrow += ((mt / p.tiles_per_group) % p.group_mod) * p.group_rows;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&a_full[sa], kTsASlotBytes);
+          tma_load_2d(a_ring + sa * kTsASlotBytes, &tmA, &a_full[sa], c * 32, mt * 128);
+          mbar_wait(&w_empty[sw], pw ^ 1);
+          mbar_arrive_expect_tx(&w_full[sw], 2 * w_half);
+          tma_load_2d(w_ring + sw * p.w_slot_bytes, &tmWh, &w_full[sw], c * 32, wrow);
+          tma_load_2d(w_ring + sw * p.w_slot_bytes + w_half, &tmWl, &w_full[sw], c * 32, wrow);
+          if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+          if (++sw == p.w_slots) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, p.NT);
+      int sw = 0, ta = 0, acc = 0;
+      uint32_t pw = 0, pta = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + acc_col0 + acc * 2 * p.NT;
+        const uint32_t d_corr = d_main + p.NT;
+        for (int c = 0; c < p.num_chunks; ++c) {
+          mbar_wait(&ta_full[ta], pta);
+          mbar_wait(&w_full[sw], pw);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + ta * 64, a_lo = a_hi + 32;
+          const uint32_t bh = smem_u32(w_ring + sw * p.w_slot_bytes), bl = bh + w_half;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            mma_tf32_ts(d_main, a_hi + j * 8, dbh, idesc, (c | j) != 0);
+            mma_tf32_ts(d_corr, a_lo + j * 8, dbh, idesc, (c | j) != 0);
+            mma_tf32_ts(d_corr, a_hi + j * 8, dbl, idesc, 1);
+          }
+          tc_commit(&ta_empty[ta]);
+          tc_commit(&w_empty[sw]);
+          if (++sw == p.w_slots) { sw = 0; pw ^= 1; }
+          ta ^= 1;
+          if (ta == 0) pta ^= 1;
+        }
+        tc_commit(&acc_full[acc]);
+        if (p.acc_sets == 2) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ============================ convert: smem fp32 -> TMEM (hi, lo) =======================
+    const int q = warp & 3;            // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;     // tile row handled by this thread (= TMEM lane)
+    int sa = 0, ta = 0;
+    uint32_t pa = 0, pta = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int c = 0; c < p.num_chunks; ++c) {
+        mbar_wait(&a_full[sa], pa);
+        mbar_wait(&ta_empty[ta], pta ^ 1);
+        tc_fence_after();
+        const float4* arow = reinterpret_cast<const float4*>(a_ring + sa * kTsASlotBytes + row * 128);
+        const uint32_t tdst = tmem_base + ta * 64 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // 16 channels at a time: 4 swizzled 16-byte chunks of the row
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = arow[(h * 4 + j) ^ (row & 7)];
+            float fh, fl;
+            split_tf32(v.x, fh, fl); hi[4 * j] = __float_as_uint(fh); lo[4 * j] = __float_as_uint(fl);
+            split_tf32(v.y, fh, fl); hi[4 * j + 1] = __float_as_uint(fh); lo[4 * j + 1] = __float_as_uint(fl);
+            split_tf32(v.z, fh, fl); hi[4 * j + 2] = __float_as_uint(fh); lo[4 * j + 2] = __float_as_uint(fl);
+            split_tf32(v.w, fh, fl); hi[4 * j + 3] = __float_as_uint(fh); lo[4 * j + 3] = __float_as_uint(fl);
+          }
+          tmem_st_32x16(tdst + h * 16, hi);
+          tmem_st_32x16(tdst + 32 + h * 16, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_empty[sa]);  // smem slot can be refilled: nothing else reads A from smem
+          mbar_arrive(&ta_full[ta]);
+        }
+        if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
+        ta ^= 1;
+        if (ta == 0) pta ^= 1;
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
+      const int n0 = nt * p.NT;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc_col0 + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
+      for (int g = 0; g < p.NT; g += 16) {
+        uint32_t r[16], rs[16];
+        tmem_ld_32x16(taddr + g, r);
+        tmem_ld_32x16(taddr + p.NT + g, rs);
+        tmem_ld_wait();
+        if (g + 16 >= p.NT) {  // last group read: hand the accumulators back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+              make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]),
+                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]));
+        __syncwarp();
+        const int j = lane & 3;
+        const int col = n0 + g + j * 4;
+        if (col < p.N) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+          for (int rb = 0; rb < 4; ++rb) {
+            const int rl = rb * 8 + (lane >> 2);
+            const long long grow = (long long)mt * 128 + q * 32 + rl;
+            if (grow < p.M) {
+              float4 o = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
+              o.x += b.x;
+              o.y += b.y;
+              o.z += b.z;
+              o.w += b.w;
+              if (p.R) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.R + grow * p.ldr + col));
+                o.x += rr.x;
+                o.y += rr.y;
+                o.z += rr.z;
+                o.w += rr.w;
+              }
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (p.acc_sets == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// Output-channel tile of the TS kernel: <= 96 keeps two accumulator sets (128 + 4*NT <= 512 columns).
+inline int ts_tile_n(int N) {
+  const int Np = (N + 15) & ~15;
+  if (Np <= 96) return Np;
+  for (int parts = 2; parts <= 16; ++parts)
+    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 96) return Np / parts;
+  if (Np <= 128) return Np;  // e.g. 112: single accumulator set
+  return 0;
+}
+
+inline int launch_gemm_ts(cudaStream_t s, const float* A, int lda, const float* w_hi, const float* w_lo,
+                          uint64_t w_rows, const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N,
+                          int K, int relu, int tiles_per_group, int group_mod, int group_rows) {
+  if (!g_tc_ready) return -20;
+  TsParams p;
+  p.bias = bias;
+  p.R = R;
+  p.C = C;
+  p.ldr = ldr;
+  p.ldc = ldc;
+  p.M = M;
+  p.N = N;
+  p.NT = ts_tile_n(N);
+  if (!p.NT) return -21;
+  p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
+  p.num_chunks = (K + 31) / 32;
+  p.relu = relu;
+  p.acc_sets = (128 + 4 * p.NT <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < 128 + p.acc_sets * 2 * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  p.a_slots = 4;
+  p.w_slot_bytes = 2 * p.NT * 128;
+  p.w_slots = (kPwMaxSmem - 1024 - 512 - 8192 - p.a_slots * kTsASlotBytes) / p.w_slot_bytes;
+  if (p.w_slots > 8) p.w_slots = 8;
+  if (p.w_slots < 2) return -22;
+  p.tiles_per_group = tiles_per_group;
+  p.group_mod = group_mod;
+  p.group_rows = group_rows;
+  CUtensorMap tmA, tmWh, tmWl;
+  int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmWh, w_hi, w_rows, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmWl, w_lo, w_rows, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  const int tiles = ((M + 127) / 128) * p.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int smem_bytes = p.a_slots * kTsASlotBytes + p.w_slots * p.w_slot_bytes + 1024 + 512 + 8192;
+  gemm_ts_kernel<<<grid, kTsThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
+  return 0;
+}
+
+// elementwise tf32 split of a device array (template features for the TS correlation)
+__global__ void split_hi_lo_kernel(const float4* __restrict__ src, float4* __restrict__ hi, float4* __restrict__ lo,
+                                   long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(src + i);
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x);
+  split_tf32(v.y, h.y, l.y);
+  split_tf32(v.z, h.z, l.z);
+  split_tf32(v.w, h.w, l.w);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+  // 227 KB opt-in limit minus static/driver slack
+
 // Output-channel tile for a layer: largest divisor-style tile <= 256 that is a multiple of 16.
 inline int pw_tile_n(int N) {
   // <= 128 so that 2 buffers x (main + correction) accumulators fit the 512 TMEM columns
@@ -526,7 +863,8 @@ inline bool pw_supported(int cin, int cout) {
 }
 
 inline int init_pw() {
-  if (cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }

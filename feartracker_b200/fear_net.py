@@ -267,6 +267,50 @@ class FEARNet(nn.Module):
         maps, boxes = self._track(search, template_features, want_maps=with_maps, want_boxes=True)
         return (boxes, maps) if with_maps else boxes
 
+    def track_boxes_from_host(self, search_host: torch.Tensor, template_features_host: torch.Tensor,
+                              out_host: Optional[torch.Tensor] = None, chunks: int = 4) -> torch.Tensor:
+        """End-to-end batched call on PINNED host buffers: the batch is cut into ``chunks`` slices whose
+        host->device copies run on a side stream while the previous slice computes, and the 48-byte box
+        records of the whole batch are copied back (to ``out_host`` if given).  No host synchronisation:
+        the caller synchronises the current stream (or the returned device tensor) when it needs the boxes."""
+        dev = next(self.parameters()).device
+        if self.training or dev.type != "cuda":
+            raise RuntimeError("track_boxes_from_host needs the model in eval mode on a CUDA device")
+        b = search_host.shape[0]
+        bz = template_features_host.shape[0]
+        chunks = max(1, min(chunks, b))
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage = {}
+        key = (b, bz, chunks)
+        if key not in self._stage:
+            bounds = [(i * b // chunks, (i + 1) * b // chunks) for i in range(chunks)]
+            self._stage = {key: dict(
+                bounds=bounds,
+                x=[torch.empty((e - s, 3, 256, 256), device=dev) for s, e in bounds],
+                z=torch.empty((bz, 256, 8, 8), device=dev),
+                boxes=torch.empty((b, _lib.BOX_DTYPE.itemsize), device=dev, dtype=torch.uint8),
+                ready=[torch.cuda.Event() for _ in bounds], free=[torch.cuda.Event() for _ in bounds],
+                zready=torch.cuda.Event())}
+        st = self._stage[key]
+        copy = self._copy_stream
+        copy.wait_stream(comp)  # staging buffers of the previous call are no longer being read
+        with torch.cuda.stream(copy):
+            st["z"].copy_(template_features_host, non_blocking=True)
+            st["zready"].record(copy)
+            for i, (s0, e0) in enumerate(st["bounds"]):
+                st["x"][i].copy_(search_host[s0:e0], non_blocking=True)
+                st["ready"][i].record(copy)
+        comp.wait_event(st["zready"])
+        for i, (s0, e0) in enumerate(st["bounds"]):
+            comp.wait_event(st["ready"][i])
+            zf = st["z"] if bz == 1 else st["z"][s0:e0]
+            st["boxes"][s0:e0] = self.track_boxes(st["x"][i], zf)
+        if out_host is not None:
+            out_host.copy_(st["boxes"], non_blocking=True)
+        return st["boxes"]
+
     @staticmethod
     def boxes_to_numpy(boxes: torch.Tensor) -> np.ndarray:
         return boxes.cpu().numpy().view(_lib.BOX_DTYPE).reshape(-1)

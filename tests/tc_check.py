@@ -86,8 +86,9 @@ def main():
     if mode == "corr":
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 3
         Bz = int(sys.argv[3]) if len(sys.argv) > 3 else B
+        impl = sys.argv[4] if len(sys.argv) > 4 else "tcgen05"
         res["ffma"] = corr_case(lib, B, Bz, "ffma")
-        res["tcgen05"] = corr_case(lib, B, Bz, "tcgen05")
+        res["tcgen05"] = corr_case(lib, B, Bz, impl)
     elif mode == "net":
         res.update(net_case(sys.argv[2], sys.argv[3]))
     print("TC_CHECK " + json.dumps(res), flush=True)
