@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--corr", default=None, help="correlation kernel implementation: ffma | tcgen05")
     ap.add_argument("--pw", default=None, help="1x1-conv implementation: ffma | tcgen05")
-    ap.add_argument("--dw", default=None, help="depthwise implementation: pixel | strip")
+    ap.add_argument("--dw", default=None, help="depthwise implementation: pixel | strip | roll | auto")
+    ap.add_argument("--early-sub", type=int, default=None, help="sub-batch (frames) of the high-resolution blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -210,6 +211,8 @@ def main():
         net.set_option("pw", args.pw)
     if args.dw:
         net.set_option("dw", args.dw)
+    if args.early_sub is not None:
+        net.set_option("early_sub", str(args.early_sub))
 
     zt, xt = synthetic_batch(B, rank)
     x_host, z_dev = xt.pin_memory(), net.get_features(zt.to(dev))
@@ -312,7 +315,8 @@ def main():
                             "config 4 at 8 GPUs), FEAR-XS checkpoint weights",
                 "global_batch": total, "per_gpu_batch": B, "parallelism": f"frames sharded over {world} rank(s)",
                 "l2": "inputs larger than L2 (201 MB search batch per step; >2 GB of workspace traffic per step)",
-                "impl": {"corr": args.corr or "default", "pw": args.pw or "default", "dw": args.dw or "default"},
+                "impl": {"corr": args.corr or "default", "pw": args.pw or "default", "dw": args.dw or "default",
+                         "early_sub": args.early_sub},
             },
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + zf_host.numel() * 4),

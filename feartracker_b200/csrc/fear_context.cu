@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,11 +60,13 @@ static const char* kStageNames[ST_COUNT] = {"stem",    "backbone_pw", "backbone_
 enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 A-from-smem | tcgen05 A-from-TMEM
 
 struct Options {
-  int corr = IMPL_FFMA;
-  int pw = IMPL_FFMA;
-  int dw = 0;  // 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
+  int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
+  int pw = -1;
+  int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
+  int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
 };
 static Options g_default_options;
+static inline int effective(int impl) { return impl >= 0 ? impl : (tc::available() ? IMPL_TC : IMPL_FFMA); }
 
 struct PwW {
   const float* w = nullptr;  // [cout][cin]
@@ -111,6 +114,7 @@ struct FearContext {
   float* ws = nullptr;
   // backbone ping-pong (per frame sizes in floats)
   float *bufX = nullptr, *bufY = nullptr, *bufE = nullptr, *bufD = nullptr;
+  float* bufS = nullptr;  // output of the early (sub-batched) blocks: 32 x 32 x 32 per frame
   // head
   float *hF = nullptr, *hT = nullptr, *hCAT[2] = {nullptr, nullptr}, *hD[2] = {nullptr, nullptr}, *hP = nullptr;
   float* hQ[2] = {nullptr, nullptr};  // tower outputs: [0] = bbox tower (x_reg), [1] = cls tower
@@ -179,14 +183,26 @@ static int launch_gemm_ffma(FearContext* c, int stage, cudaStream_t s, const flo
 // 1x1 conv over M pixels: out = act(A * W^T + b (+R)).
 static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, int lda, const PwW& w, const float* R,
                      int ldr, float* C, int ldc, int M, int relu) {
-  if (c->opt.pw == IMPL_TS && tc::pw_supported(w.cin, w.cout) && tc::ts_tile_n(w.cout)) {
+  const int pw_impl = effective(c->opt.pw);
+  if (pw_impl != IMPL_FFMA && lda == w.cin && ldc == w.cout && (!R || ldr == w.cout) &&
+      ((w.cin == 16 && w.cout == 16) || (w.cin == 24 && w.cout == 24))) {
+    // streaming layers: one pixel per thread on CUDA cores beats a tensor-core tile pipeline here
+    LaunchScope scope(c, stage, s);
+    const unsigned blocks = (unsigned)((M + 255) / 256);
+    if (w.cin == 16)
+      pw_small_kernel<16, 16><<<blocks, 256, 0, s>>>(A, w.w, w.b, R, C, M, relu);
+    else
+      pw_small_kernel<24, 24><<<blocks, 256, 0, s>>>(A, w.w, w.b, R, C, M, relu);
+    return check_launch("pw_small_kernel");
+  }
+  if (pw_impl == IMPL_TS && tc::pw_supported(w.cin, w.cout) && tc::ts_tile_n(w.cout)) {
     LaunchScope scope(c, stage, s);
     int r = tc::launch_gemm_ts(s, A, lda, w.w_hi, w.w_lo, (uint64_t)w.cout, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu,
                                0, 1, 0);
     if (r) return set_err(r, "tcgen05 (TS) pw launch failed (%d)", r);
     return check_launch("tc::gemm_ts");
   }
-  if (c->opt.pw == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
+  if (pw_impl == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
     LaunchScope scope(c, stage, s);
     int r = tc::launch_pw(s, A, lda, w.w_hi, w.w_lo, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
     if (r) return set_err(r, "tcgen05 pw launch failed (%d)", r);
@@ -278,7 +294,8 @@ static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int
 // `groups` consecutive [B][256][320] buffers starting at cat share the templates (head: cls + reg branch).
 static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B,
                        int groups, float* zth = nullptr, float* ztl = nullptr) {
-  if (opt.corr == IMPL_TS && zth && ztl) {
+  const int corr_impl = effective(opt.corr);
+  if (corr_impl == IMPL_TS && zth && ztl) {
     {
       LaunchScope scope(c, ST_LAYOUT, s);  // template features -> tf32 (hi, lo) planes
       const long long n4 = (long long)Bz * kCorrC * kFeatC / 4;
@@ -292,7 +309,7 @@ static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const
     if (r) return set_err(r, "tcgen05 (TS) corr launch failed (%d)", r);
     return check_launch("tc::gemm_ts(corr)");
   }
-  if (opt.corr == IMPL_TC || opt.corr == IMPL_TS) {
+  if (corr_impl == IMPL_TC || corr_impl == IMPL_TS) {
     LaunchScope scope(c, ST_CORR, s);
     int r = tc::launch_corr(s, zt, Bz, cat, B, groups);
     if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
@@ -309,16 +326,12 @@ static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const
 
 // ------------------------------------------------------------------------------ executor
 // img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer)
-static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, const float** feat) {
-  {
-    LaunchScope scope(c, ST_STEM, s);
-    const long long total = (long long)B * (H / 2) * (W / 2);
-    stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(img, c->stem_w, c->stem_b, c->bufX, B, H, W);
-    FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
-  }
-  int h = H / 2, w = W / 2;
-  float *X = c->bufX, *Y = c->bufY;
-  for (int i = 0; i < kNumBlocks; ++i) {
+// Run backbone blocks [first, last) on NHWC activations X (B frames of h x w).  The last block's output goes to
+// `final_out` when given (else into a ping-pong buffer); *out receives the output pointer, h/w are updated.
+static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, int& w, int first, int last,
+                      float* final_out, float** out) {
+  float* Y = (X == c->bufX) ? c->bufY : c->bufX;
+  for (int i = first; i < last; ++i) {
     const IrfSpec& sp = kBlocks[i];
     const BlockW& bw = c->blocks[i];
     const int M = B * h * w;
@@ -330,14 +343,45 @@ static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B,
     FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
     h /= sp.stride;
     w /= sp.stride;
-    const int Mo = B * h * w;
-    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, Y,
-                       sp.cout, Mo, 0));
-    float* t = X;
-    X = Y;
-    Y = t;
+    float* dst = (i == last - 1 && final_out) ? final_out : Y;
+    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, dst,
+                       sp.cout, B * h * w, 0));
+    if (dst == Y) Y = (X == c->bufS) ? ((Y == c->bufX) ? c->bufY : c->bufX) : X;
+    X = dst;
   }
-  *feat = X;
+  *out = X;
+  return 0;
+}
+
+constexpr int kEarlyBlocks = 5;  // xif1_0 .. xif3_0: the high-resolution part (128^2 / 64^2 maps at 256^2 input)
+
+// img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer).
+// With opt.early_sub > 0 the high-resolution blocks run in sub-batches of that many frames so that their
+// (6x expanded) intermediates stay resident in the 126 MB L2 instead of round-tripping through HBM.
+static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, const float** feat) {
+  const int sub = (c->opt.early_sub > 0 && c->opt.early_sub < B) ? c->opt.early_sub : B;
+  const bool blocked = sub < B;
+  const int eh = H / 8, ew = W / 8;                      // map size after the early blocks (stride 8)
+  const long long per_frame_s = (long long)eh * ew * kBlocks[kEarlyBlocks - 1].cout;
+  float* X = nullptr;
+  int h = H / 2, w = W / 2;
+  for (int b0 = 0; b0 < B; b0 += sub) {
+    const int nb = (B - b0 < sub) ? B - b0 : sub;
+    {
+      LaunchScope scope(c, ST_STEM, s);
+      const long long total = (long long)nb * (H / 2) * (W / 2);
+      stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(img + (long long)b0 * 3 * H * W, c->stem_w,
+                                                                            c->stem_b, c->bufX, nb, H, W);
+      FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
+    }
+    h = H / 2;
+    w = W / 2;
+    FEAR_TRY(run_blocks(c, s, c->bufX, nb, h, w, 0, kEarlyBlocks, blocked ? c->bufS + b0 * per_frame_s : nullptr, &X));
+  }
+  if (blocked) X = c->bufS;
+  float* out = nullptr;
+  FEAR_TRY(run_blocks(c, s, X, B, h, w, kEarlyBlocks, kNumBlocks, nullptr, &out));
+  *feat = out;
   return 0;
 }
 
@@ -576,6 +620,7 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
       (int64_t)kTmplPix * kFeatC,                                   // zt
       4 * kScorePix, kScorePix,                                     // mapB mapC
       (int64_t)kTmplPix * kFeatC, (int64_t)kTmplPix * kFeatC,       // zth ztl
+      32 * 32 * 32,                                                 // bufS
   };
   int64_t total = 0;
   std::vector<int64_t> offs;
@@ -606,6 +651,7 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
   c->mapC = p + offs[15];
   c->zth = p + offs[16];
   c->ztl = p + offs[17];
+  c->bufS = p + offs[18];
   c->reserved = max_batch;
   return 0;
 }
@@ -749,7 +795,7 @@ extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B
   if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   float *zth = nullptr, *ztl = nullptr;
-  if (g_default_options.corr == IMPL_TS) {
+  if (effective(g_default_options.corr) == IMPL_TS) {
     const size_t need = 2 * (size_t)Bz * kCorrC * kFeatC;
     FEAR_TRY(ensure_scratch2(need));
     zth = g_scratch2;
@@ -847,6 +893,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "early_sub")) {
+    o.early_sub = atoi(value);
+    return 0;
+  }
   if (!strcmp(key, "dw")) {
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
@@ -859,8 +909,9 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
   else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;
   else if (!strcmp(value, "tcgen05ts")) impl = IMPL_TS;
-  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (ffma | tcgen05 | tcgen05ts)", value);
-  if (impl != IMPL_FFMA && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
+  else if (!strcmp(value, "auto")) impl = -1;
+  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (auto | ffma | tcgen05 | tcgen05ts)", value);
+  if (impl > IMPL_FFMA && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
   if (!strcmp(key, "corr")) o.corr = impl;
   else if (!strcmp(key, "pw")) o.pw = impl;
   else return set_err(FEAR_EINVAL, "unknown option '%s' (corr | pw)", key);

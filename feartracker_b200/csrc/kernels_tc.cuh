@@ -25,6 +25,7 @@
 // a 4-stage smem ring (4 x 48 KB) keeps ~96 KB of loads in flight per SM.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -37,12 +38,15 @@ constexpr int kCorrABytes = 128 * 128;         // [128 pixels][32 ch] fp32
 constexpr int kCorrBBytes = 64 * 128;          // [64 template cells][32 ch] fp32
 constexpr int kCorrStageBytes = 2 * (kCorrABytes + kCorrBBytes);
 constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
-constexpr int kCorrThreads = 320;
+constexpr int kCorrThreads = 448;  // producer, MMA, 8 split warps, 4 epilogue warps
+constexpr int kCorrSplitThreads = 256;
 constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) columns
 
 __global__ void __launch_bounds__(kCorrThreads, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               float* __restrict__ cat, int num_frames, int z_mod) {
+               float* __restrict__ cat, int num_frames, int z_mod, int exp_mode) {
+  // exp_mode (PERF EXPERIMENTS ONLY, results wrong): 1 = skip the split arithmetic, 2 = one MMA per K-step,
+  // 4 = skip the epilogue stores.  0 in production.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes);
@@ -68,7 +72,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 64) {
     for (int s = 0; s < kCorrStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], 4);
+      mbar_init(&split[s], kCorrSplitThreads / 32);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -130,8 +134,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
             // so the (truncating) tensor-core adder rounds the big sum 3x less often
             mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
+            if (!(exp_mode & 2)) {
+              mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
+              mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
+            }
           }
           tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
           if (++stage == kCorrStages) {
@@ -144,9 +150,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kCorrSplitThreads / 32) {
     // ===================================== operand split ====================================
-    const int ts = threadIdx.x - 64;  // 0..127
+    const int ts = threadIdx.x - 64;  // 0..255
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -154,29 +160,31 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[stage], phase);
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
         float4* al = reinterpret_cast<float4*>(a_lo(stage));
+        if (!(exp_mode & 1)) {
 #pragma unroll
-        for (int i = 0; i < kCorrABytes / 16 / 128; ++i) {
-          const float4 v = ah[ts + i * 128];
-          float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          ah[ts + i * 128] = h;
-          al[ts + i * 128] = l;
-        }
-        float4* bh = reinterpret_cast<float4*>(b_hi(stage));
-        float4* bl = reinterpret_cast<float4*>(b_lo(stage));
+          for (int i = 0; i < kCorrABytes / 16 / kCorrSplitThreads; ++i) {
+            const float4 v = ah[ts + i * kCorrSplitThreads];
+            // kind::tf32 reads only the top 19 bits of each word, so the raw tile already IS the hi operand
+            // (verified on B200: identical results with and without rewriting it); only lo is materialised.
+            float4 h, l;
+            split_tf32_trunc(v.x, h.x, l.x);
+            split_tf32_trunc(v.y, h.y, l.y);
+            split_tf32_trunc(v.z, h.z, l.z);
+            split_tf32_trunc(v.w, h.w, l.w);
+            al[ts + i * kCorrSplitThreads] = l;
+          }
+          float4* bh = reinterpret_cast<float4*>(b_hi(stage));
+          float4* bl = reinterpret_cast<float4*>(b_lo(stage));
 #pragma unroll
-        for (int i = 0; i < kCorrBBytes / 16 / 128; ++i) {
-          const float4 v = bh[ts + i * 128];
-          float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          bh[ts + i * 128] = h;
-          bl[ts + i * 128] = l;
+          for (int i = 0; i < kCorrBBytes / 16 / kCorrSplitThreads; ++i) {
+            const float4 v = bh[ts + i * kCorrSplitThreads];
+            float4 h, l;
+            split_tf32_trunc(v.x, h.x, l.x);
+            split_tf32_trunc(v.y, h.y, l.y);
+            split_tf32_trunc(v.z, h.z, l.z);
+            split_tf32_trunc(v.w, h.w, l.w);
+            bl[ts + i * kCorrSplitThreads] = l;
+          }
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -223,7 +231,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int rb = 0; rb < 4; ++rb) {
           const int rl = rb * 8 + (lane >> 2);
-          *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
+          if (!(exp_mode & 4))
+            *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
         }
         __syncwarp();
       }
@@ -272,13 +281,19 @@ inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int 
   if (!g_tc_ready) return -20;
   CUtensorMap tmA, tmB;
   const int frames = B * groups;
-  int r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
+  int r;
+  if (getenv("FEAR_EXP_CONTIG"))  // PERF EXPERIMENT ONLY (wrong results): A boxes contiguous in memory
+    r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256 * 10, 32, 32, 128, kCorrChunk);
+  else
+    r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
   if (r) return r;
   r = make_tmap_2d(&tmB, zt, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
   if (r) return r;
   const int tiles = frames * 2;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  corr_tc_kernel<<<grid, kCorrThreads, kCorrSmemBytes, s>>>(tmA, tmB, cat, frames, Bz == 1 ? 0 : B);
+  int exp_mode = 0;
+  if (const char* e = getenv("FEAR_EXP_MODE")) exp_mode = atoi(e);
+  corr_tc_kernel<<<grid, kCorrThreads, kCorrSmemBytes, s>>>(tmA, tmB, cat, frames, Bz == 1 ? 0 : B, exp_mode);
   return 0;
 }
 
@@ -299,7 +314,7 @@ struct PwParams {
   int M, N, NT, num_n_tiles, num_chunks, relu, stages, stage_bytes, tmem_cols;
 };
 
-constexpr int kPwThreads = 320;
+constexpr int kPwThreads = 448;  // producer, MMA, 8 split warps, 4 epilogue warps
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
@@ -333,7 +348,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 64) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], 4);
+      mbar_init(&split[s], 8);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -404,8 +419,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp < 6) {
-    const int ts = threadIdx.x - 64;
+  } else if (warp < 10) {
+    const int ts = threadIdx.x - 64;  // 0..255
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -414,15 +429,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
         float4* al = reinterpret_cast<float4*>(a_lo(stage));
 #pragma unroll
-        for (int i = 0; i < kCorrABytes / 16 / 128; ++i) {
-          const float4 v = ah[ts + i * 128];
+        for (int i = 0; i < kCorrABytes / 16 / 256; ++i) {
+          const float4 v = ah[ts + i * 256];  // the raw tile is the hi operand as it stands (hardware truncation)
           float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          ah[ts + i * 128] = h;
-          al[ts + i * 128] = l;
+          split_tf32_trunc(v.x, h.x, l.x);
+          split_tf32_trunc(v.y, h.y, l.y);
+          split_tf32_trunc(v.z, h.z, l.z);
+          split_tf32_trunc(v.w, h.w, l.w);
+          al[ts + i * 256] = l;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -809,16 +823,26 @@ inline int launch_gemm_ts(cudaStream_t s, const float* A, int lda, const float* 
   int cols = 32;
   while (cols < 128 + p.acc_sets * 2 * p.NT) cols <<= 1;
   p.tmem_cols = cols;
-  p.a_slots = 4;
   p.w_slot_bytes = 2 * p.NT * 128;
-  p.w_slots = (kPwMaxSmem - 1024 - 512 - 8192 - p.a_slots * kTsASlotBytes) / p.w_slot_bytes;
+  // A (activations, HBM latency) gets the deep ring; B (weights / templates, mostly L2 hits) needs few slots
+  const int budget = kPwMaxSmem - 1024 - 512 - 8192;
+  p.w_slots = 3;
+  p.a_slots = (budget - p.w_slots * p.w_slot_bytes) / kTsASlotBytes;
+  if (p.a_slots > 8) p.a_slots = 8;
+  if (const char* e = getenv("FEAR_TS_ASLOTS")) p.a_slots = atoi(e);
+  if (p.a_slots < 2) return -22;
+  p.w_slots = (budget - p.a_slots * kTsASlotBytes) / p.w_slot_bytes;
   if (p.w_slots > 8) p.w_slots = 8;
   if (p.w_slots < 2) return -22;
   p.tiles_per_group = tiles_per_group;
   p.group_mod = group_mod;
   p.group_rows = group_rows;
   CUtensorMap tmA, tmWh, tmWl;
-  int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
+  int r;
+  if (getenv("FEAR_EXP_CONTIG"))  // PERF EXPERIMENT ONLY (wrong results): A boxes contiguous in memory
+    r = make_tmap_2d(&tmA, A, (uint64_t)M * (lda / 32), 32, 32, 128, 32);
+  else
+    r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
   if (r) return r;
   r = make_tmap_2d(&tmWh, w_hi, w_rows, (uint64_t)K, (uint64_t)K, p.NT, 32);
   if (r) return r;

@@ -250,5 +250,12 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
+// Truncation split: hi = v with the 13 low mantissa bits cleared (exactly what kind::tf32 reads from a raw
+// fp32 word), lo = v - hi (exact in fp32; the tensor core then drops lo's own low bits: |err| <= 2^-21 |v|).
+__device__ __forceinline__ void split_tf32_trunc(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+
 }  // namespace tc
 }  // namespace fear

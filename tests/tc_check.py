@@ -79,6 +79,25 @@ def net_case(pw, corr):
     return res
 
 
+def corr_perf(lib, impl, B=256, iters=50):
+    """Timing only: the channels-last correlation kernel on B frames, rotating over 4 buffers (> L2)."""
+    _lib.check(lib.fear_set_option(None, b"corr", impl.encode()), "fear_set_option")
+    zt = torch.randn(B, 64, 256, device="cuda")
+    cats = [torch.randn(B, 256, 320, device="cuda") for _ in range(4)]
+    st = torch.cuda.current_stream().cuda_stream
+    for c in cats:
+        _lib.check(lib.fear_corr_nhwc_f32(zt.data_ptr(), B, c.data_ptr(), B, st), "corr")
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        _lib.check(lib.fear_corr_nhwc_f32(zt.data_ptr(), B, cats[i % 4].data_ptr(), B, st), "corr")
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / iters
+    return {"impl": impl, "us": us, "GBps": 393216 * B / us * 1e-3}
+
+
 def main():
     mode = sys.argv[1]
     lib = _lib.init(0)
@@ -89,6 +108,8 @@ def main():
         impl = sys.argv[4] if len(sys.argv) > 4 else "tcgen05"
         res["ffma"] = corr_case(lib, B, Bz, "ffma")
         res["tcgen05"] = corr_case(lib, B, Bz, impl)
+    elif mode == "corrperf":
+        res["perf"] = [corr_perf(lib, impl) for impl in sys.argv[2:]]
     elif mode == "net":
         res.update(net_case(sys.argv[2], sys.argv[3]))
     print("TC_CHECK " + json.dumps(res), flush=True)

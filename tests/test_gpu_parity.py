@@ -96,7 +96,7 @@ def test_backbone_block_by_block(net, sd64):
         report[name] = [e1, e2]
         worst = max(worst, e2)
     _dump("backbone_blocks.json", report)
-    assert worst < 1e-4, report
+    assert worst < 2e-5, report
 
 
 def test_get_features_and_feature_extractor(net, sd64):
@@ -106,13 +106,13 @@ def test_get_features_and_feature_extractor(net, sd64):
     assert zf.shape == (2, 256, 8, 8)
     zt4, _, _, _ = fo.synthetic_crops(4)
     zf4 = net.get_features(zt4.cuda()).cpu().numpy()
-    assert_maps_close(zf4, g["zf64"], "template features", inf_tol=1e-5)
+    assert_maps_close(zf4, g["zf64"], "template features", tol=2e-2, inf_tol=2e-5)
     col = {}
     fo.get_features(sd64, xt.double(), col)
     fe = net.feature_extractor(xt.cuda())
     assert fe.shape == (2, 112, 16, 16)
-    assert_maps_close(fe.cpu().numpy(), col["xif4_7"].numpy(), "feature_extractor", inf_tol=1e-5)
-    assert_maps_close(net.get_features(xt.cuda()).cpu().numpy(), col["neck"].numpy(), "search features", inf_tol=1e-5)
+    assert_maps_close(fe.cpu().numpy(), col["xif4_7"].numpy(), "feature_extractor", tol=2e-2, inf_tol=2e-5)
+    assert_maps_close(net.get_features(xt.cuda()).cpu().numpy(), col["neck"].numpy(), "search features", tol=2e-2, inf_tol=2e-5)
 
 
 def test_head_intermediates(net, sd64):
@@ -133,7 +133,7 @@ def test_head_intermediates(net, sd64):
     assert all(v[1] < 1e-4 for v in report.values()), report
     bbox, cls, cls_dw, x_reg = net.connect_model(xf.float().cuda(), zf.float().cuda())
     assert torch.equal(bbox, out[R]) and cls_dw.shape == (2, 256, 16, 16)
-    assert_maps_close(x_reg.cpu().numpy(), col["x_reg"].numpy(), "x_reg", inf_tol=1e-5)
+    assert_maps_close(x_reg.cpu().numpy(), col["x_reg"].numpy(), "x_reg", tol=2e-2, inf_tol=5e-5)
 
 
 def test_forward_seed0_golden(net):
@@ -195,7 +195,7 @@ def test_teacher_forced_video_frames(net):
     g = golden("video_teacher.npz")
     trk = fb.FEARTracker(net, cuda_id=0, **fb.FEAR_XS_TRACKER_KWARGS)
     zf = net.get_features(trk._preprocess_image(g["template_crop"]))
-    assert_maps_close(zf.cpu().numpy(), g["template_features"], "template features", inf_tol=1e-5)
+    assert_maps_close(zf.cpu().numpy(), g["template_features"], "template features", tol=2e-2, inf_tol=2e-5)
     for i, crop in enumerate(g["search_crops"]):
         out = net.track(trk._preprocess_image(crop), zf)
         assert_maps_close(out[R].cpu().numpy(), g["reg64"][i:i + 1], f"reg frame {g['frames'][i]}")
@@ -241,6 +241,22 @@ def test_depthwise_variants_are_bit_identical(net, impl):
         zf2 = net.get_features(zt.cuda())
         out = net.track(xt.cuda(), zf2)
     finally:
-        net.set_option("dw", "pixel")
+        net.set_option("dw", "auto")
     assert torch.equal(zf, zf2)
     assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
+
+
+def test_l2_sub_batching_is_bit_identical(net):
+    """Running the high-resolution blocks in sub-batches (L2 blocking) must not change a single bit."""
+    zt, xt, _, _ = fo.synthetic_crops(4)
+    x = xt.cuda().repeat(2, 1, 1, 1)[:7]
+    zf = net.get_features(zt.cuda()).repeat(2, 1, 1, 1)[:7]
+    ref = net.track(x, zf)
+    net.set_option("early_sub", "2")
+    try:
+        out = net.track(x, zf)
+        zf2 = net.get_features(zt.cuda())
+    finally:
+        net.set_option("early_sub", "0")
+    assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
+    assert torch.equal(zf2, zf[:4])
