@@ -66,6 +66,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, str(gpu_index)
+        self.mark_a = self.mark_b = None
 
     def __enter__(self):
         try:
@@ -81,6 +82,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout and self.proc is not None:
+            time.sleep(0.05)
+
+    def begin(self):
+        self.mark_a = len(self.rows)
+
+    def end(self):
+        time.sleep(0.25)  # let the sample(s) covering the end of the timed region arrive
+        self.mark_b = len(self.rows)
+
     def __exit__(self, *a):
         if self.proc:
             self.proc.terminate()
@@ -90,11 +103,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        a = max(0, (self.mark_a or 0) - 1)
+        rows = self.rows[a:self.mark_b] if self.mark_b is not None else self.rows[a:]
+        rows = rows or self.rows[-3:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for n, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -250,12 +266,21 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    clocks = ClockSampler(local_rank).__enter__()
     for _ in range(args.warmup):
         step_device()
+    clocks.wait_first_sample()
     l0 = net.launch_count()
-    with ClockSampler(local_rank) as clocks:
-        ms_total = timed(step_device, args.steps)
-    launches = (net.launch_count() - l0) // args.steps
+    clocks.begin()
+    ms_total = timed(step_device, args.steps)
+    if ms_total < 400.0:  # keep the GPU under the same load until nvidia-smi (100 ms period) has sampled it
+        extra = int(400.0 / (ms_total / args.steps)) + 1
+        for _ in range(extra):
+            step_device()
+        torch.cuda.synchronize(dev)
+    clocks.end()
+    clocks.__exit__()
+    launches = (net.launch_count() - l0) // (args.steps + (extra if ms_total < 400.0 else 0))
     fps = total * args.steps / (ms_total * 1e-3)
 
     for _ in range(args.warmup):

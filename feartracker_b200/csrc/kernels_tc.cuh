@@ -311,10 +311,10 @@ struct PwParams {
   const float* R;     // residual [M][ldr] or null
   float* C;
   int ldr, ldc;
-  int M, N, NT, num_n_tiles, num_chunks, relu, stages, stage_bytes, tmem_cols;
+  int M, N, NT, num_n_tiles, num_chunks, last_ksteps, relu, stages, stage_bytes, tmem_cols;
 };
 
-constexpr int kPwThreads = 448;  // producer, MMA, 8 split warps, 4 epilogue warps
+constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
@@ -329,7 +329,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_full = bars + 3 * S;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 8 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_tiles = (p.M + 127) >> 7;
@@ -353,7 +353,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], 8);
     }
     fence_mbar_init();
   }
@@ -400,8 +400,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(stage));
           const uint32_t bh = smem_u32(w_hi(stage)), bl = smem_u32(w_lo(stage));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          const int ksteps = (c == p.num_chunks - 1) ? p.last_ksteps : 4;  // K tail: skip all-zero K-steps
+          for (int j = 0; j < ksteps; ++j) {
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
@@ -448,9 +448,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
+    // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups
     const int q = warp & 3;
+    const int hsel = (warp - 10) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4* stg = reinterpret_cast<float4*>(epi_stage + (warp - 10) * 2048);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
       const int n0 = nt * p.NT;
@@ -459,8 +462,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
       // Per-warp 32 x 16 staging tile (2 KB, XOR-swizzled 16-byte chunks): the accumulator arrives one
       // row per lane; it leaves as 8 rows x 64 contiguous bytes per store instruction (full sectors).
-      float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
-      for (int g = 0; g < p.NT; g += 16) {
+      for (int g = hsel * 16; g < p.NT; g += 32) {
         uint32_t r[16], rs[16];
         tmem_ld_32x16(taddr + g, r);
         tmem_ld_32x16(taddr + p.NT + g, rs);
@@ -911,9 +913,10 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   if (!p.NT) return -21;
   p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
   p.num_chunks = (K + 31) / 32;
+  p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
   p.relu = relu;
   p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
-  p.stages = (kPwMaxSmem - 1024 - 256 - 8192) / p.stage_bytes;
+  p.stages = (kPwMaxSmem - 1024 - 256 - 16384) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return -22;
   int cols = 32;
@@ -928,7 +931,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   if (r) return r;
   const int tiles = ((M + 127) / 128) * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256 + 8192;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256 + 16384;
   pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
   return 0;
 }

@@ -147,7 +147,7 @@ def test_forward_seed0_golden(net):
     e_cls = assert_maps_close(out[C].cpu().numpy(), g["cls64"], "cls")
     assert int(out[C].flatten().argmax()) == 104
     zf = net.get_features(z.cuda())
-    assert_maps_close(zf.cpu().numpy(), g["zf64"], "zf")
+    assert_maps_close(zf.cpu().numpy(), g["zf64"], "zf", tol=2e-2, inf_tol=2e-5)  # intermediate: inf-norm bound
     trk = net.track(x.cuda(), zf)
     assert torch.equal(trk[R], out[R]) and torch.equal(trk[C], out[C])  # forward == track, like the reference
     _dump("seed0_errors.json", {"reg": e_reg, "cls": e_cls})
