@@ -62,6 +62,7 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 
 struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
+  int fuse = 1;       // fused pw-expand + depthwise kernels for the stride-2 blocks
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
 };
@@ -282,6 +283,43 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   return check_launch("dw_conv_nhwc_kernel");
 }
 
+// Fused pw-expand + depthwise for the stride-2 blocks; returns 1 if this block shape has no fused kernel.
+template <int CIN, int MID, int MSL, int K, int TH, int TW>
+static int launch_fused_one(FearContext* c, cudaStream_t s, const float* X, const BlockW& bw, float* D, int B, int H,
+                            int W) {
+  constexpr int THREADS = 512;
+  constexpr int smem = fused_expand_dw_smem_bytes<CIN, MID, MSL, K, TH, TW>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(fused_expand_dw_s2_kernel<CIN, MID, MSL, K, TH, TW, THREADS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int Ho = H / 2, Wo = W / 2;
+  if (Ho % TH || Wo % TW) return 1;
+  LaunchScope scope(c, ST_BACKBONE_DW, s);
+  const unsigned grid = (unsigned)(B * (Ho / TH) * (Wo / TW));
+  fused_expand_dw_s2_kernel<CIN, MID, MSL, K, TH, TW, THREADS><<<grid, THREADS, smem, s>>>(X, bw.pw.w, bw.pw.b, bw.dw.w,
+                                                                                   bw.dw.b, D, H, W);
+  return check_launch("fused_expand_dw_s2_kernel");
+}
+
+static int launch_fused_expand_dw(FearContext* c, cudaStream_t s, const IrfSpec& sp, const float* X, const BlockW& bw,
+                                  float* D, int B, int H, int W) {
+  if (sp.stride != 2 || !sp.has_pw()) return 1;
+  // (tile, resident channel slice) per block: keep the halo recompute factor low and >= 2 CTAs per SM where possible
+  if (sp.cin == 16 && sp.mid() == 96 && sp.k == 3) return launch_fused_one<16, 96, 96, 3, 8, 4>(c, s, X, bw, D, B, H, W);
+  if (sp.cin == 24 && sp.mid() == 144 && sp.k == 5) {
+    if ((H / 2) % 8 == 0) return launch_fused_one<24, 144, 48, 5, 8, 8>(c, s, X, bw, D, B, H, W);
+    return launch_fused_one<24, 144, 48, 5, 4, 4>(c, s, X, bw, D, B, H, W);
+  }
+  if (sp.cin == 32 && sp.mid() == 192 && sp.k == 5) {
+    if ((H / 2) % 8 == 0) return launch_fused_one<32, 192, 32, 5, 8, 8>(c, s, X, bw, D, B, H, W);
+    return launch_fused_one<32, 192, 32, 5, 4, 4>(c, s, X, bw, D, B, H, W);
+  }
+  return 1;
+}
+
 static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int ldin, long long sIn, float* out,
                             int ldout, long long sOut, int R, int Cn, int batch) {
   LaunchScope scope(c, ST_LAYOUT, s);
@@ -335,12 +373,19 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
     const IrfSpec& sp = kBlocks[i];
     const BlockW& bw = c->blocks[i];
     const int M = B * h * w;
-    const float* E = X;
-    if (sp.has_pw()) {
-      FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
-      E = c->bufE;
+    int fused = 1;
+    if (c->opt.fuse) {
+      fused = launch_fused_expand_dw(c, s, sp, X, bw, c->bufD, B, h, w);
+      if (fused < 0 || fused > 1) return fused;
     }
-    FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
+    if (fused == 1) {  // unfused: materialise the expanded tensor, then the depthwise conv
+      const float* E = X;
+      if (sp.has_pw()) {
+        FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
+        E = c->bufE;
+      }
+      FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
+    }
     h /= sp.stride;
     w /= sp.stride;
     float* dst = (i == last - 1 && final_out) ? final_out : Y;
@@ -893,6 +938,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "fuse")) {
+    o.fuse = atoi(value) != 0;
+    return 0;
+  }
   if (!strcmp(key, "early_sub")) {
     o.early_sub = atoi(value);
     return 0;

@@ -359,6 +359,142 @@ __global__ void __launch_bounds__(256) gemm_nt_ffma_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused inverted-residual front half for the stride-2 blocks (xif2_0, xif3_0, xif4_0):
+//     D = ReLU(dw_KxK_s2(ReLU(X * W1^T + b1)) + b2)
+// The 6x-expanded tensor E = ReLU(X*W1^T + b1) (1.6 GB per 256-frame step for xif2_0 alone) never leaves
+// the SM: each CTA takes a TH x TW tile of OUTPUT pixels, stages the (2TH+K-2) x (2TW+K-2) input patch of X,
+// expands it into shared memory with CUDA cores (Cin is only 16..32 here, so this is ~1 FLOP per byte of
+// the unfused traffic), then runs the depthwise stride-2 window over the resident tile and writes D.
+// Pixels of the patch that fall outside the image are forced to 0 (the depthwise conv zero-pads E, and
+// E(0-input) = ReLU(b1) != 0).
+// ------------------------------------------------------------------------------------------
+template <int CIN, int MID, int MSL, int K, int TH, int TW, int THREADS>
+__global__ void __launch_bounds__(THREADS) fused_expand_dw_s2_kernel(
+    const float* __restrict__ X, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ wd, const float* __restrict__ bd, float* __restrict__ D, int H, int W) {
+  // MSL = channels of the expanded tensor resident at a time (MID / MSL passes over the same input patch):
+  // a smaller slice buys a larger spatial tile, i.e. less halo recomputation for the 5x5 blocks.
+  static_assert(MID % MSL == 0 && MSL % 4 == 0 && CIN % 4 == 0, "channel slicing");
+  constexpr int P = K / 2;
+  constexpr int IH = 2 * TH + K - 2, IW = 2 * TW + K - 2, NPIX = IH * IW;
+  constexpr int C4 = MSL / 4, K4 = CIN / 4;
+  extern __shared__ __align__(16) float fsm[];
+  float* sX = fsm;                        // [NPIX][CIN]
+  float* sW1 = sX + NPIX * CIN;           // [CIN][MID]  (transposed: channel-contiguous per k)
+  float* sB1 = sW1 + CIN * MID;           // [MID]
+  float* sWd = sB1 + MID;                 // [K*K][MID]
+  float* sBd = sWd + K * K * MID;         // [MID]
+  float* sE = sBd + MID;                  // [NPIX][MSL]
+  const int tid = threadIdx.x;
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles_x = Wo / TW, tiles_y = Ho / TH;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const int iy0 = 2 * oy0 - P, ix0 = 2 * ox0 - P;
+
+  // ---- stage weights and the input patch --------------------------------------------------
+  for (int i = tid; i < CIN * MID; i += THREADS) {
+    const int o = i / CIN, k = i - o * CIN;  // w1 is [MID][CIN]
+    sW1[k * MID + o] = __ldg(w1 + i);
+  }
+  for (int i = tid; i < MID; i += THREADS) {
+    sB1[i] = __ldg(b1 + i);
+    sBd[i] = __ldg(bd + i);
+  }
+  for (int i = tid; i < K * K * MID; i += THREADS) sWd[i] = __ldg(wd + i);
+  const float* Xb = X + (long long)b * H * W * CIN;
+  for (int i = tid; i < NPIX * K4; i += THREADS) {
+    const int p = i / K4, q = i - p * K4;
+    const int iy = iy0 + p / IW, ix = ix0 + p % IW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(Xb + ((long long)iy * W + ix) * CIN) + q);
+    reinterpret_cast<float4*>(sX)[i] = v;
+  }
+  __syncthreads();
+
+  float* Db = D + (long long)b * Ho * Wo * MID;
+  constexpr int PG = (NPIX + 3) / 4;
+#pragma unroll 1
+  for (int m0 = 0; m0 < MID; m0 += MSL) {
+    // ---- expand: E[p][c] = ReLU(b1[c] + sum_k X[p][k] W1[c][k]), 4 pixels x 4 channels per work item ----
+    for (int u = tid; u < PG * C4; u += THREADS) {
+      const int c4 = u % C4, pg = u / C4;
+      const int ch = m0 + 4 * c4;
+      const float4 bb = *reinterpret_cast<const float4*>(sB1 + ch);
+      float4 acc[4] = {bb, bb, bb, bb};
+#pragma unroll
+      for (int kq = 0; kq < K4; ++kq) {
+        float4 xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = pg * 4 + j;
+          xv[j] = (p < NPIX) ? *reinterpret_cast<const float4*>(sX + p * CIN + 4 * kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 wv = *reinterpret_cast<const float4*>(sW1 + (4 * kq + kk) * MID + ch);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xs = kk == 0 ? xv[j].x : kk == 1 ? xv[j].y : kk == 2 ? xv[j].z : xv[j].w;
+            acc[j].x = fmaf(xs, wv.x, acc[j].x);
+            acc[j].y = fmaf(xs, wv.y, acc[j].y);
+            acc[j].z = fmaf(xs, wv.z, acc[j].z);
+            acc[j].w = fmaf(xs, wv.w, acc[j].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = pg * 4 + j;
+        if (p < NPIX) {
+          const int iy = iy0 + p / IW, ix = ix0 + p % IW;
+          const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
+          float4 e = make_float4(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f), fmaxf(acc[j].z, 0.f), fmaxf(acc[j].w, 0.f));
+          if (!inside) e = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sE + p * MSL + 4 * c4) = e;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- depthwise KxK stride 2 over the resident slice -------------------------------------
+    for (int u = tid; u < TH * TW * C4; u += THREADS) {
+      const int c4 = u % C4, op = u / C4;
+      const int oy = op / TW, ox = op % TW;
+      const int ch = m0 + 4 * c4;
+      float4 acc = *reinterpret_cast<const float4*>(sBd + ch);
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float4 e = *reinterpret_cast<const float4*>(sE + ((2 * oy + ky) * IW + 2 * ox + kx) * MSL + 4 * c4);
+          const float4 k = *reinterpret_cast<const float4*>(sWd + (ky * K + kx) * MID + ch);
+          acc.x = fmaf(e.x, k.x, acc.x);
+          acc.y = fmaf(e.y, k.y, acc.y);
+          acc.z = fmaf(e.z, k.z, acc.z);
+          acc.w = fmaf(e.w, k.w, acc.w);
+        }
+      acc.x = fmaxf(acc.x, 0.f);
+      acc.y = fmaxf(acc.y, 0.f);
+      acc.z = fmaxf(acc.z, 0.f);
+      acc.w = fmaxf(acc.w, 0.f);
+      *reinterpret_cast<float4*>(Db + ((long long)(oy0 + oy) * Wo + ox0 + ox) * MID + ch) = acc;
+    }
+    __syncthreads();  // the slice buffer is rewritten by the next pass
+  }
+}
+
+template <int CIN, int MID, int MSL, int K, int TH, int TW>
+constexpr int fused_expand_dw_smem_bytes() {
+  constexpr int NPIX = (2 * TH + K - 2) * (2 * TW + K - 2);
+  return 4 * (NPIX * CIN + CIN * MID + MID + K * K * MID + MID + NPIX * MSL);
+}
+
+// ------------------------------------------------------------------------------------------
 // Tiny 1x1 convs (Cin, Cout <= 32: xif1_0.pwl 16->16, xif2_2/2_3.pwl 24->24) are pure streaming:
 // ~1 FLOP per byte, millions of pixels.  A tensor-core tile pipeline only adds per-tile latency there
 // (measured: 585 us vs the 125 us HBM time), so these run one pixel per thread on CUDA cores with the
