@@ -62,7 +62,7 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 
 struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
-  int fuse = 1;       // fused pw-expand + depthwise kernels for the stride-2 blocks
+  int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
 };
@@ -223,6 +223,26 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   float4* o4 = reinterpret_cast<float4*>(out);
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
+  // shared-memory tiled kernel: stride 1, maps that are multiples of 16x16, channels in 32-slabs
+  const bool want_tile = (c->opt.dw == 4 || (c->opt.dw == 3 && w.k == 5)) && stride == 1 && H % 16 == 0 && W % 16 == 0 &&
+                         C4 % 8 == 0 && ((relu && bias) || (!relu && !bias));
+  if (want_tile) {
+    const unsigned blocks = (unsigned)(B * (H / 16) * (W / 16) * (C4 / 8));
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(dw_conv_tile_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    dw_tile_smem_bytes<5>()));
+      attr_done = true;
+    }
+    if (w.k == 5 && relu)
+      dw_conv_tile_kernel<5, true, true><<<blocks, 256, dw_tile_smem_bytes<5>(), s>>>(i4, w4, b4, o4, H, W, C4);
+    else if (w.k == 3 && relu)
+      dw_conv_tile_kernel<3, true, true><<<blocks, 256, dw_tile_smem_bytes<3>(), s>>>(i4, w4, b4, o4, H, W, C4);
+    else if (w.k == 3)
+      dw_conv_tile_kernel<3, false, false><<<blocks, 256, dw_tile_smem_bytes<3>(), s>>>(i4, w4, b4, o4, H, W, C4);
+    else return set_err(FEAR_EINVAL, "unsupported tiled depthwise config k=%d", w.k);
+    return check_launch("dw_conv_tile_kernel");
+  }
   const bool want_roll = c->opt.dw == 2 || (c->opt.dw == 3 && w.k == 3 && stride == 1);
   if (want_roll && Wo % 4 == 0 && (H / stride) % 16 == 0) {
     // rolling-window kernels: TX output columns x 16 output rows per thread, weights in registers
@@ -950,8 +970,9 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
     else if (!strcmp(value, "roll")) o.dw = 2;
-    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, strip otherwise
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | auto)", value);
+    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: smem tile for 5x5 s1, rolling window for 3x3 s1
+    else if (!strcmp(value, "tile")) o.dw = 4;
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | auto)", value);
     return 0;
   }
   int impl;

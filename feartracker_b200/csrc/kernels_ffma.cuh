@@ -359,6 +359,90 @@ __global__ void __launch_bounds__(256) gemm_nt_ffma_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Depthwise KxK stride-1 conv, shared-memory tiled: one CTA = one frame x 16x16 output tile x 32-channel
+// slab.  The (16+K-1)^2 x 32-channel input patch is staged once in shared memory (coalesced 128-byte
+// rows, zero halo), so every input value is fetched from L2/HBM exactly once per tile instead of being
+// re-requested through L1 by up to K*K neighbouring threads (the strip kernel moves ~2.5x the algorithmic
+// bytes through L2 on the 16x16 stage).  Each thread owns 4 channels x 8 consecutive pixels of a row;
+// per kernel row it reads 8+K-1 inputs and K weights from shared memory for 8*K FMA4.
+// Accumulation order per output is the same as in the other depthwise kernels (bit-identical results).
+// ------------------------------------------------------------------------------------------
+template <int K, bool RELU, bool BIAS>
+__global__ void __launch_bounds__(256, 2) dw_conv_tile_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
+                                                           const float4* __restrict__ bias, float4* __restrict__ out,
+                                                           int H, int W, int C4) {
+  constexpr int T = 16, TX = 8, P = K / 2, IT = T + K - 1, CS4 = 8;  // 32-channel slab = 8 float4
+  extern __shared__ __align__(16) float4 dw_tile_smem[];
+  float4* sIn = dw_tile_smem;              // [IT * IT][CS4]
+  float4* sW = sIn + IT * IT * CS4;        // [K * K][CS4]
+  const int tid = threadIdx.x;
+  const int slabs = C4 / CS4;
+  const int tiles_x = W / T, tiles_y = H / T;
+  int t = blockIdx.x;
+  const int slab = t % slabs;
+  t /= slabs;
+  const int tx = t % tiles_x;
+  t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int c40 = slab * CS4;
+  const int y0 = ty * T - P, x0 = tx * T - P;
+  const float4* inb = in + (long long)b * H * W * C4 + c40;
+  for (int i = tid; i < IT * IT * CS4; i += 256) {
+    const int q = i % CS4, p = i / CS4;
+    const int iy = y0 + p / IT, ix = x0 + p % IT;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(inb + ((long long)iy * W + ix) * C4 + q);
+    sIn[i] = v;
+  }
+  for (int i = tid; i < K * K * CS4; i += 256) sW[i] = __ldg(w + (i / CS4) * C4 + c40 + (i % CS4));
+  __syncthreads();
+
+  const int q = tid % CS4;           // channel group inside the slab
+  const int strip = tid / CS4;       // 32 strips: 16 rows x 2 half-rows
+  const int oy = strip >> 1, ox0 = (strip & 1) * TX;
+  const float4 b4 = BIAS ? __ldg(bias + c40 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[TX];
+#pragma unroll
+  for (int i = 0; i < TX; ++i) acc[i] = b4;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float4 v[TX + K - 1];
+    const float4* row = sIn + ((oy + ky) * IT + ox0) * CS4 + q;
+#pragma unroll
+    for (int i = 0; i < TX + K - 1; ++i) v[i] = row[i * CS4];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 k = sW[(ky * K + kx) * CS4 + q];
+#pragma unroll
+      for (int i = 0; i < TX; ++i) {
+        acc[i].x = fmaf(v[i + kx].x, k.x, acc[i].x);
+        acc[i].y = fmaf(v[i + kx].y, k.y, acc[i].y);
+        acc[i].z = fmaf(v[i + kx].z, k.z, acc[i].z);
+        acc[i].w = fmaf(v[i + kx].w, k.w, acc[i].w);
+      }
+    }
+  }
+  float4* o = out + (long long)b * H * W * C4 + ((long long)(ty * T + oy) * W + tx * T + ox0) * C4 + c40 + q;
+#pragma unroll
+  for (int i = 0; i < TX; ++i) {
+    float4 r = acc[i];
+    if (RELU) {
+      r.x = fmaxf(r.x, 0.f);
+      r.y = fmaxf(r.y, 0.f);
+      r.z = fmaxf(r.z, 0.f);
+      r.w = fmaxf(r.w, 0.f);
+    }
+    o[(long long)i * C4] = r;
+  }
+}
+
+template <int K>
+constexpr int dw_tile_smem_bytes() {
+  return 16 * ((16 + K - 1) * (16 + K - 1) * 8 + K * K * 8);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused inverted-residual front half for the stride-2 blocks (xif2_0, xif3_0, xif4_0):
 //     D = ReLU(dw_KxK_s2(ReLU(X * W1^T + b1)) + b2)
 // The 6x-expanded tensor E = ReLU(X*W1^T + b1) (1.6 GB per 256-frame step for xif2_0 alone) never leaves

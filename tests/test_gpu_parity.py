@@ -229,7 +229,7 @@ def test_free_running_video_trajectory(net):
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
 
 
-@pytest.mark.parametrize("impl", ["strip", "roll"])
+@pytest.mark.parametrize("impl", ["strip", "roll", "tile"])
 def test_depthwise_variants_are_bit_identical(net, impl):
     """The register-strip / rolling-window depthwise kernels accumulate in the same order as the per-pixel one."""
     zt, xt, _, _ = fo.synthetic_crops(2)
@@ -260,3 +260,18 @@ def test_l2_sub_batching_is_bit_identical(net):
         net.set_option("early_sub", "0")
     assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
     assert torch.equal(zf2, zf[:4])
+
+
+def test_fused_expand_depthwise_blocks(net, sd64):
+    """Optional fused pw-expand + depthwise kernels (stride-2 blocks): same activations as the unfused path."""
+    _, xt, _, _ = fo.synthetic_crops(2)
+    col = {}
+    fo.get_features(sd64, xt.double(), col)
+    net.set_option("fuse", "1")
+    try:
+        got = {n: net.backbone_prefix(xt.cuda(), i).cpu().numpy() for n, i in (("xif2_0", 2), ("xif3_0", 5), ("xif4_0", 9))}
+    finally:
+        net.set_option("fuse", "0")
+    for name, a in got.items():
+        e1, e2 = map_errors(a, col[name].numpy())
+        assert e2 < 2e-5, (name, e1, e2)
