@@ -224,7 +224,7 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
   // shared-memory tiled kernel: stride 1, maps that are multiples of 16x16, channels in 32-slabs
-  const bool want_tile = (c->opt.dw == 4 || (c->opt.dw == 3 && w.k == 5)) && stride == 1 && H % 16 == 0 && W % 16 == 0 &&
+  const bool want_tile = c->opt.dw == 4 && stride == 1 && H % 16 == 0 && W % 16 == 0 &&
                          C4 % 8 == 0 && ((relu && bias) || (!relu && !bias));
   if (want_tile) {
     const unsigned blocks = (unsigned)(B * (H / 16) * (W / 16) * (C4 / 8));
@@ -970,7 +970,7 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
     else if (!strcmp(value, "roll")) o.dw = 2;
-    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: smem tile for 5x5 s1, rolling window for 3x3 s1
+    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, register strip otherwise
     else if (!strcmp(value, "tile")) o.dw = 4;
     else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | auto)", value);
     return 0;
