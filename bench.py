@@ -214,6 +214,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version at VERSION/INFO)
         dist.init_process_group("nccl", device_id=dev)
     B, total = args.batch, args.batch * world
 
