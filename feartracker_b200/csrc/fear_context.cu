@@ -265,6 +265,26 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
 #undef ROLL_CASE
     return check_launch("dw_conv_roll_kernel");
   }
+  if ((c->opt.dw == 5 || (c->opt.dw == 3 && w.k == 5)) && Wo % 4 == 0) {
+    // L1-blocked strip layout: CTA = 32 channels x 4 strips x 8 rows
+    const int TX = stride == 1 ? 4 : 2;
+    const int strips = Wo / TX;
+    const unsigned blocks = (unsigned)((long long)B * (((H / stride) + 7) / 8) * ((strips + 3) / 4) * ((C4 + 7) / 8));
+    if (w.k == 3 && stride == 1 && relu && bias)
+      dw_conv_strip_blocked_kernel<3, 1, 4, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 3 && stride == 2 && relu && bias)
+      dw_conv_strip_blocked_kernel<3, 2, 2, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 5 && stride == 1 && relu && bias)
+      dw_conv_strip_blocked_kernel<5, 1, 4, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 5 && stride == 2 && relu && bias)
+      dw_conv_strip_blocked_kernel<5, 2, 2, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else if (w.k == 3 && stride == 1 && !relu && !bias)
+      dw_conv_strip_blocked_kernel<3, 1, 4, false, false><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
+    else
+      return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
+                     (int)bias);
+    return check_launch("dw_conv_strip_blocked_kernel");
+  }
   if (c->opt.dw >= 1 && Wo % 4 == 0) {
     // register-strip kernels: 4 outputs per thread (stride 1) / 2 outputs per thread (stride 2)
     const int TX = stride == 1 ? 4 : 2;
@@ -418,12 +438,25 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
   return 0;
 }
 
+static StemNorm imagenet_norm() {
+  // float32 arithmetic exactly as albumentations.Normalize does it (reference base_tracker.py:73)
+  StemNorm n;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int i = 0; i < 3; ++i) {
+    volatile float m = mean[i] * 255.0f, sd = stdv[i] * 255.0f;
+    n.mean[i] = m;
+    n.inv[i] = 1.0f / sd;
+  }
+  return n;
+}
+
 constexpr int kEarlyBlocks = 5;  // xif1_0 .. xif3_0: the high-resolution part (128^2 / 64^2 maps at 256^2 input)
 
 // img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer).
 // With opt.early_sub > 0 the high-resolution blocks run in sub-batches of that many frames so that their
 // (6x expanded) intermediates stay resident in the 126 MB L2 instead of round-tripping through HBM.
-static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, const float** feat) {
+static int run_backbone(FearContext* c, cudaStream_t s, const void* img, int B, int H, int W, const float** feat,
+                        bool u8 = false) {
   const int sub = (c->opt.early_sub > 0 && c->opt.early_sub < B) ? c->opt.early_sub : B;
   const bool blocked = sub < B;
   const int eh = H / 8, ew = W / 8;                      // map size after the early blocks (stride 8)
@@ -434,9 +467,13 @@ static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B,
     const int nb = (B - b0 < sub) ? B - b0 : sub;
     {
       LaunchScope scope(c, ST_STEM, s);
-      const long long total = (long long)nb * (H / 2) * (W / 2);
-      stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(img + (long long)b0 * 3 * H * W, c->stem_w,
-                                                                            c->stem_b, c->bufX, nb, H, W);
+      const unsigned blocks = (unsigned)((long long)nb * ((H / 2 + 3) / 4) * ((W / 2 + 31) / 32));
+      if (u8)
+        stem_conv3x3s2_kernel<true><<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(img) + (long long)b0 * 3 * H * W,
+                                                           c->stem_w, c->stem_b, c->bufX, nb, H, W, imagenet_norm());
+      else
+        stem_conv3x3s2_kernel<false><<<blocks, 128, 0, s>>>(static_cast<const float*>(img) + (long long)b0 * 3 * H * W,
+                                                            c->stem_w, c->stem_b, c->bufX, nb, H, W, StemNorm());
       FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
     }
     h = H / 2;
@@ -451,9 +488,10 @@ static int run_backbone(FearContext* c, cudaStream_t s, const float* img, int B,
 }
 
 // img (B,3,H,W) NCHW -> out NHWC [B][H/16 * W/16][256]   (FEARNet.get_features, fear_net.py:63-66)
-static int run_features(FearContext* c, cudaStream_t s, const float* img, int B, int H, int W, float* out) {
+static int run_features(FearContext* c, cudaStream_t s, const void* img, int B, int H, int W, float* out,
+                        bool u8 = false) {
   const float* X = nullptr;
-  FEAR_TRY(run_backbone(c, s, img, B, H, W, &X));
+  FEAR_TRY(run_backbone(c, s, img, B, H, W, &X, u8));
   return launch_pw(c, ST_NECK, s, X, kBackboneC, c->neck, nullptr, 0, out, kFeatC, B * (H / 16) * (W / 16), 0);
 }
 
@@ -796,8 +834,9 @@ extern "C" int fear_head(FearContext* c, const float* d_zfeat, int Bz, const flo
   return 0;
 }
 
-static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, const float* d_search,
-                      const float* d_zfeat, int Bz, int B, float* d_bbox, float* d_cls, FearBox* d_boxes) {
+static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, const void* d_search,
+                      const float* d_zfeat, int Bz, int B, float* d_bbox, float* d_cls, FearBox* d_boxes,
+                      bool search_u8 = false) {
   if (d_zfeat && Bz == 1) FEAR_TRY(stage_template(c, s, d_zfeat, 1));
   for (int b0 = 0; b0 < B; b0 += c->reserved) {
     const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
@@ -810,7 +849,9 @@ static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, c
     } else {
       nz = 1;
     }
-    FEAR_TRY(run_features(c, s, d_search + (long long)b0 * 3 * 256 * 256, nb, 256, 256, c->hF));
+    const void* sp = search_u8 ? (const void*)(static_cast<const uint8_t*>(d_search) + (long long)b0 * 3 * 256 * 256)
+                               : (const void*)(static_cast<const float*>(d_search) + (long long)b0 * 3 * 256 * 256);
+    FEAR_TRY(run_features(c, s, sp, nb, 256, 256, c->hF, search_u8));
     float* bb = d_bbox ? d_bbox + (long long)b0 * 4 * kScorePix : c->mapB;
     float* cc = d_cls ? d_cls + (long long)b0 * kScorePix : c->mapC;
     FEAR_TRY(run_head(c, s, c->zt, nz, c->hF, nb, bb, cc));
@@ -826,6 +867,32 @@ extern "C" int fear_track(FearContext* c, const float* d_search, const float* d_
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
   return track_impl(c, (cudaStream_t)stream, nullptr, d_search, d_zfeat, Bz, B, d_bbox, d_cls, d_boxes);
+}
+
+extern "C" int fear_track_u8(FearContext* c, const uint8_t* d_search_u8, const float* d_zfeat, int Bz, int B,
+                             float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_search_u8 || !d_zfeat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
+  return track_impl(c, (cudaStream_t)stream, nullptr, d_search_u8, d_zfeat, Bz, B, d_bbox, d_cls, d_boxes, true);
+}
+
+extern "C" int fear_get_features_u8(FearContext* c, const uint8_t* d_img_u8, int B, int H, int W, float* d_feat,
+                                    void* stream) {
+  FEAR_TRY(check_ctx(c));
+  if (!d_img_u8 || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
+    return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int P = (H / 16) * (W / 16);
+  for (int b0 = 0; b0 < B; b0 += c->reserved) {
+    const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
+    FEAR_TRY(run_features(c, s, d_img_u8 + (long long)b0 * 3 * H * W, nb, H, W, c->hF, true));
+    FEAR_TRY(launch_transpose(c, s, c->hF, kFeatC, (long long)P * kFeatC, d_feat + (long long)b0 * kFeatC * P, P,
+                              (long long)kFeatC * P, P, kFeatC, nb));
+  }
+  return 0;
 }
 
 extern "C" int fear_forward(FearContext* c, const float* d_template, const float* d_search, int B, float* d_bbox,
@@ -909,8 +976,8 @@ extern "C" int fear_debug_backbone_prefix(FearContext* c, const float* d_img, in
   cudaStream_t s = (cudaStream_t)stream;
   {
     LaunchScope scope(c, ST_STEM, s);
-    const long long total = (long long)B * (H / 2) * (W / 2);
-    stem_conv3x3s2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_img, c->stem_w, c->stem_b, c->bufX, B, H, W);
+    const unsigned blocks = (unsigned)((long long)B * ((H / 2 + 3) / 4) * ((W / 2 + 31) / 32));
+    stem_conv3x3s2_kernel<false><<<blocks, 128, 0, s>>>(d_img, c->stem_w, c->stem_b, c->bufX, B, H, W, StemNorm());
     FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
   }
   int h = H / 2, w = W / 2, ch = kStemC;
@@ -972,7 +1039,8 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     else if (!strcmp(value, "roll")) o.dw = 2;
     else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, register strip otherwise
     else if (!strcmp(value, "tile")) o.dw = 4;
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | auto)", value);
+    else if (!strcmp(value, "blocked")) o.dw = 5;
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | blocked | auto)", value);
     return 0;
   }
   int impl;

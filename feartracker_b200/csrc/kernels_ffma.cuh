@@ -17,25 +17,40 @@ namespace fear {
 // (fbnet_c xif0_0; reference call site fear_net.py:58-61.)  One thread per output pixel, all 16
 // output channels in registers; the 432 weights are broadcast from shared memory.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) stem_conv3x3s2_kernel(const float* __restrict__ img, const float* __restrict__ w,
+// U8 = true: img is a uint8 HWC crop (B,H,W,3) as the tracker holds it; the ImageNet normalisation of
+// Tracker._preprocess_image (reference base_tracker.py:69-81,97-103: (x - mean*255) * (1/(std*255)), float32,
+// subtract then multiply) is applied on the fly with the same two roundings, so the result is bit-identical
+// to normalising on the host while the host->device copy shrinks 4x.
+struct StemNorm {
+  float mean[3], inv[3];
+};
+template <bool U8>
+__global__ void __launch_bounds__(128) stem_conv3x3s2_kernel(const void* __restrict__ img_, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                             int B, int H, int W) {
+                                                             int B, int H, int W, StemNorm nrm) {
   __shared__ float sw[27 * 16];
   __shared__ float sb[16];
   for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
+  // CTA = 32 output columns x 4 output rows (one warp per row): vertically adjacent rows share an input
+  // row, which now hits L1 instead of being re-read from L2 by another CTA.
   const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)B * Ho * Wo;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = (int)(idx % Wo);
-  const int oy = (int)((idx / Wo) % Ho);
-  const int b = (int)(idx / ((long long)Wo * Ho));
+  const int xg = (Wo + 31) / 32, yg = (Ho + 3) / 4;
+  int t = blockIdx.x;
+  const int bx = t % xg;
+  t /= xg;
+  const int by = t % yg;
+  const int b = t / yg;
+  const int ox = bx * 32 + (threadIdx.x & 31);
+  const int oy = by * 4 + (threadIdx.x >> 5);
+  if (ox >= Wo || oy >= Ho || b >= B) return;
+  const long long idx = ((long long)b * Ho + oy) * Wo + ox;
   float acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = sb[c];
-  const float* base = img + (long long)b * 3 * H * W;
+  const float* base = static_cast<const float*>(img_) + (long long)b * 3 * H * W;
+  const uint8_t* base8 = static_cast<const uint8_t*>(img_) + (long long)b * 3 * H * W;
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
@@ -45,7 +60,12 @@ __global__ void __launch_bounds__(128) stem_conv3x3s2_kernel(const float* __rest
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 - 1 + kx;
         float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(base + ((long long)ci * H + iy) * W + ix);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          if (U8)
+            v = __fmul_rn(__fsub_rn((float)__ldg(base8 + ((long long)iy * W + ix) * 3 + ci), nrm.mean[ci]), nrm.inv[ci]);
+          else
+            v = __ldg(base + ((long long)ci * H + iy) * W + ix);
+        }
         const float* wr = sw + (ci * 9 + ky * 3 + kx) * 16;
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
@@ -172,6 +192,82 @@ __global__ void __launch_bounds__(256) dw_conv_strip_kernel(const float4* __rest
       r.w = fmaxf(r.w, 0.f);
     }
     o[(long long)t * C4] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Register-strip depthwise conv with an L1-friendly thread layout.  Same arithmetic as
+// dw_conv_strip_kernel, but a CTA now owns a compact patch -- 8 channel groups (32 channels) x 4 adjacent
+// strips x 8 output rows -- instead of 256 consecutive channel groups of one strip.  Neighbouring rows and
+// strips share (K-1)/K of their inputs, and with this layout those re-reads hit L1 (ncu showed the flat
+// layout pulling ~2.5x the algorithmic bytes through L2 on the 5x5 layers).  A warp covers 8 channel
+// groups of 4 strips in one row => each load instruction touches four 128-byte segments.
+// ------------------------------------------------------------------------------------------
+template <int K, int S, int TX, bool RELU, bool BIAS>
+__global__ void __launch_bounds__(256) dw_conv_strip_blocked_kernel(const float4* __restrict__ in,
+                                                                    const float4* __restrict__ w,
+                                                                    const float4* __restrict__ bias,
+                                                                    float4* __restrict__ out, int B, int H, int W,
+                                                                    int C4) {
+  const int Ho = H / S, Wo = W / S;
+  const int strips = Wo / TX;
+  const int sgroups = (strips + 3) / 4, rgroups = (Ho + 7) / 8, cgroups = (C4 + 7) / 8;
+  int t = blockIdx.x;
+  const int cg = t % cgroups;
+  t /= cgroups;
+  const int sg = t % sgroups;
+  t /= sgroups;
+  const int rg = t % rgroups;
+  const int b = t / rgroups;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int c4 = cg * 8 + (lane & 7);
+  const int sx = sg * 4 + (lane >> 3);
+  const int oy = rg * 8 + wrp;
+  if (c4 >= C4 || sx >= strips || oy >= Ho) return;
+  constexpr int P = K / 2;
+  constexpr int NIN = (TX - 1) * S + K;
+  const int ox0 = sx * TX;
+  const int ix0 = ox0 * S - P;
+  float4 acc[TX];
+  const float4 b4 = BIAS ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < TX; ++i) acc[i] = b4;
+  const float4* inb = in + (long long)b * H * W * C4 + c4;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = oy * S - P + ky;
+    if (iy < 0 || iy >= H) continue;
+    const float4* row = inb + (long long)iy * W * C4;
+    float4 v[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) {
+      const int ix = ix0 + i;
+      v[i] = (ix >= 0 && ix < W) ? __ldg(row + (long long)ix * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 k = __ldg(w + (ky * K + kx) * C4 + c4);
+#pragma unroll
+      for (int i = 0; i < TX; ++i) {
+        const float4 x = v[i * S + kx];
+        acc[i].x = fmaf(x.x, k.x, acc[i].x);
+        acc[i].y = fmaf(x.y, k.y, acc[i].y);
+        acc[i].z = fmaf(x.z, k.z, acc[i].z);
+        acc[i].w = fmaf(x.w, k.w, acc[i].w);
+      }
+    }
+  }
+  float4* o = out + (((long long)b * Ho + oy) * Wo + ox0) * C4 + c4;
+#pragma unroll
+  for (int i = 0; i < TX; ++i) {
+    float4 r = acc[i];
+    if (RELU) {
+      r.x = fmaxf(r.x, 0.f);
+      r.y = fmaxf(r.y, 0.f);
+      r.z = fmaxf(r.z, 0.f);
+      r.w = fmaxf(r.w, 0.f);
+    }
+    o[(long long)i * C4] = r;
   }
 }
 

@@ -220,7 +220,17 @@ class FEARNet(nn.Module):
         return out
 
     def get_features(self, crop: torch.Tensor) -> torch.Tensor:
-        """(B,3,H,W) -> (B,256,H/16,W/16)."""
+        """(B,3,H,W) float -> (B,256,H/16,W/16).  A uint8 (B,H,W,3) RGB crop is also accepted: it is
+        ImageNet-normalised inside the stem kernel (bit-identical to Tracker._preprocess_image on the host)."""
+        if crop.dtype == torch.uint8:
+            x, h, lib = self._prep(crop, keep_dtype=True)
+            b, hh, ww, ch = x.shape
+            if ch != 3:
+                raise ValueError(f"uint8 crops must be (B,H,W,3), got {tuple(x.shape)}")
+            out = torch.empty((b, 256, hh // 16, ww // 16), device=x.device, dtype=torch.float32)
+            _lib.check(lib.fear_get_features_u8(h, x.data_ptr(), b, hh, ww, out.data_ptr(), self._stream(x)),
+                       "fear_get_features_u8")
+            return out
         x, h, lib = self._prep(crop)
         b, _, hh, ww = x.shape
         out = torch.empty((b, 256, hh // 16, ww // 16), device=x.device, dtype=torch.float32)
@@ -283,12 +293,13 @@ class FEARNet(nn.Module):
         if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
             self._copy_stream = torch.cuda.Stream(dev)
             self._stage = {}
-        key = (b, bz, chunks)
+        key = (b, bz, chunks, search_host.dtype, tuple(search_host.shape[1:]))
         if key not in self._stage:
             bounds = [(i * b // chunks, (i + 1) * b // chunks) for i in range(chunks)]
             self._stage = {key: dict(
                 bounds=bounds,
-                x=[torch.empty((e - s, 3, 256, 256), device=dev) for s, e in bounds],
+                x=[torch.empty((e - s,) + tuple(search_host.shape[1:]), device=dev, dtype=search_host.dtype)
+                   for s, e in bounds],
                 z=torch.empty((bz, 256, 8, 8), device=dev),
                 boxes=torch.empty((b, _lib.BOX_DTYPE.itemsize), device=dev, dtype=torch.uint8),
                 ready=[torch.cuda.Event() for _ in bounds], free=[torch.cuda.Event() for _ in bounds],
@@ -368,20 +379,22 @@ class FEARNet(nn.Module):
 
     # ------------------------------------------------------------------ internals
     def _track(self, search, template_features, want_maps: bool, want_boxes: bool):
-        s, h, lib = self._prep(search)
+        u8 = search.dtype == torch.uint8
+        s, h, lib = self._prep(search, keep_dtype=u8)
         zf = self._as_input(template_features, s.device)
         b = s.shape[0]
         self._check_shapes(zf, b)
-        if tuple(s.shape[1:]) != (3, 256, 256):
-            raise ValueError(f"search must be (B,3,256,256), got {tuple(s.shape)}")
+        if tuple(s.shape[1:]) != ((256, 256, 3) if u8 else (3, 256, 256)):
+            raise ValueError(f"search must be float (B,3,256,256) or uint8 (B,256,256,3), got {tuple(s.shape)}")
         bbox = cls = boxes = None
         if want_maps:
             bbox = torch.empty((b, 4, 16, 16), device=s.device, dtype=torch.float32)
             cls = torch.empty((b, 1, 16, 16), device=s.device, dtype=torch.float32)
         if want_boxes:
             boxes = torch.empty((b, _lib.BOX_DTYPE.itemsize), device=s.device, dtype=torch.uint8)
+        entry = lib.fear_track_u8 if u8 else lib.fear_track
         _lib.check(
-            lib.fear_track(h, s.data_ptr(), zf.data_ptr(), zf.shape[0], b,
+            entry(h, s.data_ptr(), zf.data_ptr(), zf.shape[0], b,
                            bbox.data_ptr() if want_maps else None, cls.data_ptr() if want_maps else None,
                            boxes.data_ptr() if want_boxes else None, self._stream(s)),
             "fear_track")
@@ -403,14 +416,14 @@ class FEARNet(nn.Module):
             raise ValueError(f"all inputs must live on {device}, got {t.device}")
         return t.detach().to(torch.float32).contiguous()
 
-    def _prep(self, x: torch.Tensor):
+    def _prep(self, x: torch.Tensor, keep_dtype: bool = False):
         if self.training:
             raise NotImplementedError(
                 "FEARNet (B200) runs inference only: call .eval().  The training step (BN batch statistics, "
                 "autograd) is outside the accelerated hot path (SURVEY.md section 8(f)-3)")
         if not x.is_cuda:
             raise RuntimeError("FEARNet (B200) has no CPU path: inputs must be CUDA tensors on a B200 (sm_100)")
-        x = self._as_input(x, x.device)
+        x = x.detach().contiguous() if keep_dtype else self._as_input(x, x.device)
         h, lib = self._ensure_handle(x.device)
         if x.shape[0] > self._reserved:
             self.reserve(x.shape[0])

@@ -94,6 +94,14 @@ int fear_head(FearContext* h, const float* d_zfeat, int Bz, const float* d_xfeat
 int fear_track(FearContext* h, const float* d_search, const float* d_zfeat, int Bz, int B,
                float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);
 
+/* Same as fear_track / fear_get_features but the image is the tracker's raw uint8 RGB crop in HWC layout
+ * (B,H,W,3): the ImageNet normalisation of Tracker._preprocess_image (tracker/base_tracker.py:69-81,97-103)
+ * is applied inside the stem kernel with the same float32 roundings (bit-identical to host normalisation);
+ * the host->device copy is 4x smaller. */
+int fear_track_u8(FearContext* h, const uint8_t* d_search_u8, const float* d_zfeat, int Bz, int B,
+                  float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);
+int fear_get_features_u8(FearContext* h, const uint8_t* d_img_u8, int B, int H, int W, float* d_feat, void* stream);
+
 /* template (B,3,128,128) + search (B,3,256,256) -> maps (+ boxes). */
 int fear_forward(FearContext* h, const float* d_template, const float* d_search, int B,
                  float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);

@@ -193,7 +193,7 @@ def test_batch_chunking_and_invariance(net):
 def test_teacher_forced_video_frames(net):
     """C3 (teacher-forced): the oracle's recorded search crops -> maps within 1e-3, identical integer box."""
     g = golden("video_teacher.npz")
-    trk = fb.FEARTracker(net, cuda_id=0, **fb.FEAR_XS_TRACKER_KWARGS)
+    trk = fb.FEARTracker(net, cuda_id=0, host_normalize=True, **fb.FEAR_XS_TRACKER_KWARGS)
     zf = net.get_features(trk._preprocess_image(g["template_crop"]))
     assert_maps_close(zf.cpu().numpy(), g["template_features"], "template features", tol=2e-2, inf_tol=2e-5)
     for i, crop in enumerate(g["search_crops"]):
@@ -229,7 +229,7 @@ def test_free_running_video_trajectory(net):
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
 
 
-@pytest.mark.parametrize("impl", ["strip", "roll", "tile"])
+@pytest.mark.parametrize("impl", ["strip", "roll", "tile", "blocked"])
 def test_depthwise_variants_are_bit_identical(net, impl):
     """The register-strip / rolling-window depthwise kernels accumulate in the same order as the per-pixel one."""
     zt, xt, _, _ = fo.synthetic_crops(2)
@@ -275,3 +275,20 @@ def test_fused_expand_depthwise_blocks(net, sd64):
     for name, a in got.items():
         e1, e2 = map_errors(a, col[name].numpy())
         assert e2 < 2e-5, (name, e1, e2)
+
+
+def test_uint8_input_path_is_bit_identical(net):
+    """Raw uint8 HWC crops normalised inside the stem kernel == float crops normalised on the host."""
+    _, _, zu, xu = fo.synthetic_crops(3)
+    zt, xt, _, _ = fo.synthetic_crops(3)
+    zf_host = net.get_features(zt.cuda())
+    zf_dev = net.get_features(zu.permute(0, 2, 3, 1).contiguous().cuda())
+    assert torch.equal(zf_host, zf_dev)
+    a = net.track(xt.cuda(), zf_host)
+    b = net.track(xu.permute(0, 2, 3, 1).contiguous().cuda(), zf_host)
+    assert torch.equal(a[R], b[R]) and torch.equal(a[C], b[C])
+    boxes = net.track_boxes_from_host(xu.permute(0, 2, 3, 1).contiguous().pin_memory(), zf_host.cpu().pin_memory(), chunks=2)
+    torch.cuda.synchronize()
+    rec = net.boxes_to_numpy(boxes)
+    ref = net.boxes_to_numpy(net.track_boxes(xt.cuda(), zf_host))
+    assert (rec == ref).all()
