@@ -250,7 +250,7 @@ def main():
 
     def step_e2e(src=None):
         # public API on pinned HOST buffers: chunked H2D overlapped with compute, boxes copied back
-        boxes = net.track_boxes_from_host(xu_host if src is None else src, zf_host, chunks=4)
+        boxes = net.track_boxes_from_host(xu_host if src is None else src, zf_host)
         boxes = sharding.all_gather_boxes(boxes, total)
         box_host.copy_(boxes, non_blocking=True)
         return boxes
@@ -358,8 +358,8 @@ def main():
                     "d2h_bytes_per_step": int(box_host.numel()),
                     "api": "FEARNet.track_boxes_from_host on pinned host buffers: raw uint8 HWC crops (what "
                            "FEARTracker holds; ImageNet normalisation fused into the stem kernel, bit-identical to "
-                           "host normalisation) + fp32 template features, 4 chunks with copy/compute overlap, box "
-                           "records copied back"},
+                           "host normalisation) + fp32 template features; double-buffered staging, so the copy of step "
+                           "i+1 overlaps the kernels of step i; box records copied back every step"},
             "e2e_fp32_inputs": {"value": total * args.steps / (ms_e2e32 * 1e-3), "unit": "frames/s",
                                 "ms_per_step": ms_e2e32 / args.steps,
                                 "h2d_bytes_per_step": int(x_host.numel() * 4 + zf_host.numel() * 4),

@@ -278,11 +278,15 @@ class FEARNet(nn.Module):
         return (boxes, maps) if with_maps else boxes
 
     def track_boxes_from_host(self, search_host: torch.Tensor, template_features_host: torch.Tensor,
-                              out_host: Optional[torch.Tensor] = None, chunks: int = 4) -> torch.Tensor:
-        """End-to-end batched call on PINNED host buffers: the batch is cut into ``chunks`` slices whose
-        host->device copies run on a side stream while the previous slice computes, and the 48-byte box
-        records of the whole batch are copied back (to ``out_host`` if given).  No host synchronisation:
-        the caller synchronises the current stream (or the returned device tensor) when it needs the boxes."""
+                              out_host: Optional[torch.Tensor] = None, chunks: int = 1) -> torch.Tensor:
+        """End-to-end batched call on PINNED host buffers (uint8 (B,256,256,3) raw crops or float32
+        (B,3,256,256) normalised crops, plus float32 template features).
+
+        The host->device copies run on a side stream into one of TWO staging sets, so the copy of call i+1
+        overlaps the kernels of call i (and, with ``chunks`` > 1, the copy of slice j+1 overlaps the kernels
+        of slice j inside one call).  The 48-byte box records of the whole batch are copied back to
+        ``out_host`` if given.  No host synchronisation: synchronise the current stream (or an event) before
+        reading ``out_host`` / the returned device tensor, which stays valid until the call after next."""
         dev = next(self.parameters()).device
         if self.training or dev.type != "cuda":
             raise RuntimeError("track_boxes_from_host needs the model in eval mode on a CUDA device")
@@ -292,32 +296,43 @@ class FEARNet(nn.Module):
         comp = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
             self._copy_stream = torch.cuda.Stream(dev)
-            self._stage = {}
+            self._stage, self._stage_key, self._stage_flip = None, None, 0
         key = (b, bz, chunks, search_host.dtype, tuple(search_host.shape[1:]))
-        if key not in self._stage:
+        if self._stage_key != key:
             bounds = [(i * b // chunks, (i + 1) * b // chunks) for i in range(chunks)]
-            self._stage = {key: dict(
-                bounds=bounds,
-                x=[torch.empty((e - s,) + tuple(search_host.shape[1:]), device=dev, dtype=search_host.dtype)
-                   for s, e in bounds],
-                z=torch.empty((bz, 256, 8, 8), device=dev),
-                boxes=torch.empty((b, _lib.BOX_DTYPE.itemsize), device=dev, dtype=torch.uint8),
-                ready=[torch.cuda.Event() for _ in bounds], free=[torch.cuda.Event() for _ in bounds],
-                zready=torch.cuda.Event())}
-        st = self._stage[key]
+
+            def make_set():
+                return dict(
+                    x=[torch.empty((e - s,) + tuple(search_host.shape[1:]), device=dev, dtype=search_host.dtype)
+                       for s, e in bounds],
+                    z=torch.empty((bz, 256, 8, 8), device=dev),
+                    boxes=torch.empty((b, _lib.BOX_DTYPE.itemsize), device=dev, dtype=torch.uint8),
+                    ready=[torch.cuda.Event() for _ in bounds], zready=torch.cuda.Event(), free=torch.cuda.Event())
+
+            self._stage = dict(bounds=bounds, sets=[make_set(), make_set()])
+            self._stage_key, self._stage_flip = key, 0
+            for st in self._stage["sets"]:
+                st["free"].record(comp)
+        st = self._stage["sets"][self._stage_flip]
+        self._stage_flip ^= 1
+        bounds = self._stage["bounds"]
         copy = self._copy_stream
-        copy.wait_stream(comp)  # staging buffers of the previous call are no longer being read
+        copy.wait_event(st["free"])  # kernels of the call that last used this staging set have finished
         with torch.cuda.stream(copy):
             st["z"].copy_(template_features_host, non_blocking=True)
             st["zready"].record(copy)
-            for i, (s0, e0) in enumerate(st["bounds"]):
+            for i, (s0, e0) in enumerate(bounds):
                 st["x"][i].copy_(search_host[s0:e0], non_blocking=True)
                 st["ready"][i].record(copy)
         comp.wait_event(st["zready"])
-        for i, (s0, e0) in enumerate(st["bounds"]):
+        for i, (s0, e0) in enumerate(bounds):
             comp.wait_event(st["ready"][i])
             zf = st["z"] if bz == 1 else st["z"][s0:e0]
-            st["boxes"][s0:e0] = self.track_boxes(st["x"][i], zf)
+            if chunks == 1:
+                st["boxes"] = self.track_boxes(st["x"][i], zf)
+            else:
+                st["boxes"][s0:e0] = self.track_boxes(st["x"][i], zf)
+        st["free"].record(comp)
         if out_host is not None:
             out_host.copy_(st["boxes"], non_blocking=True)
         return st["boxes"]
