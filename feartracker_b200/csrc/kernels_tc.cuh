@@ -312,6 +312,7 @@ struct PwParams {
   float* C;
   int ldr, ldc;
   int M, N, NT, num_n_tiles, num_chunks, last_ksteps, relu, stages, stage_bytes, tmem_cols;
+  int split_acc;  // 1: hi*hi and the cross terms accumulate separately (long K); 0: one accumulator (K <= 64)
 };
 
 constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
@@ -404,9 +405,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            // short K (<= 2 chunks): a handful of accumulations, the truncating adder is harmless and a single
+            // accumulator halves the TMEM read (64 B/clk/SM) that dominates the epilogue of the wide layers
+            const uint32_t dc = p.split_acc ? d + p.NT : d;
             mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + p.NT, dal, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + p.NT, dah, dbl, idesc, 1);
+            mma_tf32_ss(dc, dal, dbh, idesc, p.split_acc ? ((c | j) != 0) : 1);
+            mma_tf32_ss(dc, dah, dbl, idesc, 1);
           }
           tc_commit(&empty[stage]);
           if (++stage == S) {
@@ -465,7 +469,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int g = hsel * 16; g < p.NT; g += 32) {
         uint32_t r[16], rs[16];
         tmem_ld_32x16(taddr + g, r);
-        tmem_ld_32x16(taddr + p.NT + g, rs);
+        if (p.split_acc) {
+          tmem_ld_32x16(taddr + p.NT + g, rs);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) rs[e] = 0u;
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -914,6 +923,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
   p.num_chunks = (K + 31) / 32;
   p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
+  p.split_acc = p.num_chunks > 2;
   p.relu = relu;
   p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
   p.stages = (kPwMaxSmem - 1024 - 256 - 16384) / p.stage_bytes;
