@@ -319,7 +319,7 @@ constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue war
 
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
-             const __grid_constant__ CUtensorMap tmWl, const PwParams p) {
+             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC, const PwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
@@ -330,7 +330,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_full = bars + 3 * S;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 8 warps x 2 KB
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;      // 8 warps x 2 buffers x 2 KB, 512-B aligned
+  float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][128] per accumulator stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_tiles = (p.M + 127) >> 7;
@@ -341,6 +342,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmWh);
     prefetch_tmap(&tmWl);
+    prefetch_tmap(&tmC);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
@@ -452,20 +454,27 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups
+    // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
+    // ncu showed these warps ~96 % busy on the wide layers (the kernel's critical path), so the common case
+    // (no residual) is kept lean: bias from shared memory, the finished 32 x 16 block is staged in the
+    // SWIZZLE_64B layout and handed to TMA (cp.async.bulk.tensor store), which also clips the M / N tails.
     const int q = warp & 3;
-    const int hsel = (warp - 10) >> 2;
+    const int ew = warp - 10;
+    const int hsel = ew >> 2;
+    const int etid = threadIdx.x - 320;  // 0..255 among the epilogue warps
     int acc = 0;
     uint32_t acc_phase = 0;
-    float4* stg = reinterpret_cast<float4*>(epi_stage + (warp - 10) * 2048);
+    int buf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
       const int n0 = nt * p.NT;
+      // bias of this tile's columns -> smem (one slot per accumulator stage); named barrier over the 8 warps
+      if (etid < p.NT) sbias[acc * 128 + etid] = (p.bias && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
-      // Per-warp 32 x 16 staging tile (2 KB, XOR-swizzled 16-byte chunks): the accumulator arrives one
-      // row per lane; it leaves as 8 rows x 64 contiguous bytes per store instruction (full sectors).
+      const float* sb = sbias + acc * 128;
       for (int g = hsel * 16; g < p.NT; g += 32) {
         uint32_t r[16], rs[16];
         tmem_ld_32x16(taddr + g, r);
@@ -475,48 +484,70 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int e = 0; e < 16; ++e) rs[e] = 0u;
         }
+        float4* stg = reinterpret_cast<float4*>(epi_stage + (ew * 2 + buf) * 2048);
+        if (!p.R) tma_store_wait_read<1>();  // the store issued two groups ago has finished reading this buffer
         tmem_ld_wait();
+        if (!p.R) {
+          // ---- lean path: bias + ReLU in registers, swizzled staging, TMA store ----
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
-              make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]),
-                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]),
-                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]));
-        __syncwarp();
-        const int j = lane & 3;
-        const int col = n0 + g + j * 4;
-        if (col < p.N) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + g + 4 * j);
+            float4 o = make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]) + b.x,
+                                   __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]) + b.y,
+                                   __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]) + b.z,
+                                   __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]) + b.w);
+            if (p.relu) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, n0 + g, mt * 128 + q * 32);
+            tma_store_commit();
+          }
+          buf ^= 1;
+        } else {
+          // ---- residual path: transpose through smem, coalesced residual loads and stores ----
 #pragma unroll
-          for (int rb = 0; rb < 4; ++rb) {
-            const int rl = rb * 8 + (lane >> 2);
-            const long long grow = (long long)mt * 128 + q * 32 + rl;
-            if (grow < p.M) {
-              float4 o = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
-              o.x += b.x;
-              o.y += b.y;
-              o.z += b.z;
-              o.w += b.w;
-              if (p.R) {
+          for (int j = 0; j < 4; ++j)
+            stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+                make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]),
+                            __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]));
+          __syncwarp();
+          const int j = lane & 3;
+          const int col = n0 + g + j * 4;
+          if (col < p.N) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + g + 4 * j);
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+              const int rl = rb * 8 + (lane >> 2);
+              const long long grow = (long long)mt * 128 + q * 32 + rl;
+              if (grow < p.M) {
+                float4 o = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(p.R + grow * p.ldr + col));
-                o.x += rr.x;
-                o.y += rr.y;
-                o.z += rr.z;
-                o.w += rr.w;
+                o.x += b.x + rr.x;
+                o.y += b.y + rr.y;
+                o.z += b.z + rr.z;
+                o.w += b.w + rr.w;
+                if (p.relu) {
+                  o.x = fmaxf(o.x, 0.f);
+                  o.y = fmaxf(o.y, 0.f);
+                  o.z = fmaxf(o.z, 0.f);
+                  o.w = fmaxf(o.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = o;
               }
-              if (p.relu) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = o;
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -524,6 +555,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (!p.R) tma_store_wait<0>();  // all bulk stores of this warp have completed before the CTA exits
   }
 
   tc_fence_before();
@@ -535,6 +567,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/driver slack
+constexpr int kPwTailBytes = 1024 /*barriers*/ + 8 * 2 * 2048 /*epilogue staging*/ + 1024 /*bias*/;
 
 // ------------------------------------------------------------------------------------------
 // gemm_ts_kernel -- second-generation tensor-core GEMM: the activation operand lives in TENSOR MEMORY.
@@ -926,7 +959,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.split_acc = p.num_chunks > 2;
   p.relu = relu;
   p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
-  p.stages = (kPwMaxSmem - 1024 - 256 - 16384) / p.stage_bytes;
+  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return -22;
   int cols = 32;
@@ -941,8 +974,11 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   if (r) return r;
   const int tiles = ((M + 127) / 128) * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256 + 16384;
-  pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
+  CUtensorMap tmC;  // output: [M][N] window of C (pitch ldc); 32 x 16 boxes, SWIZZLE_64B staging; clips the tails
+  r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
+  if (r) return r;
+  const int smem_bytes = p.stages * p.stage_bytes + 1024 + kPwTailBytes;
+  pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, tmC, p);
   return 0;
 }
 

@@ -36,7 +36,7 @@ inline int resolve_driver() {
 }
 
 // 2-D fp32 row-major tensor [rows][cols] with row pitch `pitch_floats`; box = [box_rows][box_cols];
-// 128-byte swizzle when box_cols * 4 == 128, none otherwise.
+// 128-byte swizzle when box_cols * 4 == 128, 64-byte swizzle for 64-byte rows, none otherwise.
 inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_floats,
                         uint32_t box_rows, uint32_t box_cols) {
   if (resolve_driver()) return -10;
@@ -44,7 +44,9 @@ inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
   cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMapSwizzle sw = (box_cols * 4 == 128)  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (box_cols * 4 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
