@@ -265,7 +265,7 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
 #undef ROLL_CASE
     return check_launch("dw_conv_roll_kernel");
   }
-  if ((c->opt.dw == 5 || (c->opt.dw == 3 && w.k == 5)) && Wo % 4 == 0) {
+  if (c->opt.dw == 5 && Wo % 4 == 0) {
     // L1-blocked strip layout: CTA = 32 channels x 4 strips x 8 rows
     const int TX = stride == 1 ? 4 : 2;
     const int strips = Wo / TX;
@@ -284,6 +284,13 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
       return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
                      (int)bias);
     return check_launch("dw_conv_strip_blocked_kernel");
+  }
+  if (c->opt.dw == 3 && w.k == 5 && stride == 1 && Wo % 8 == 0 && relu && bias) {
+    // 5x5 stride 1: 8 outputs per thread (12 input + 5 weight loads per 40 FMA4 and kernel row)
+    const long long total = (long long)B * H * (Wo / 8) * C4;
+    dw_conv_strip_kernel<5, 1, 8, true, true><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+        i4, w4, b4, o4, B, H, W, C4);
+    return check_launch("dw_conv_strip_kernel<5,1,8>");
   }
   if (c->opt.dw >= 1 && Wo % 4 == 0) {
     // register-strip kernels: 4 outputs per thread (stride 1) / 2 outputs per thread (stride 2)
