@@ -119,11 +119,62 @@ class FEARTracker(Tracker):
         return dict(bbox=pred_bbox)
 
     def track(self, search_crop: np.ndarray) -> Tuple[np.ndarray, float]:
-        search = self._preprocess_image(search_crop)
         if self.tracking_config.get("smooth", False):
-            return self._postprocess(self.net.track(search, self._template_features))
-        rec = self.net.boxes_to_numpy(self.net.track_boxes(search, self._template_features))[0]
+            return self._postprocess(self.net.track(self._preprocess_image(search_crop), self._template_features))
+        rec = self._track_record(search_crop)
         return np.array([rec["x"], rec["y"], rec["w"], rec["h"]]), np.float32(rec["score"])
+
+    # -- streaming fast path: persistent pinned staging + (optionally) the whole per-frame step as ONE CUDA graph --
+    def _track_record(self, search_crop: np.ndarray):
+        """One frame: crop -> pinned staging -> device -> network + on-device decode -> 48-byte box record.
+
+        The 70 kernel launches of a batch-1 step cost more host time than GPU time, so after one eager warm-up
+        call the step is captured into a CUDA graph (static input / template / output buffers; the library's
+        workspace pointers are stable) and replayed per frame.  ``cuda_graph=False`` in the tracking config keeps
+        eager launches."""
+        dev = self._device()
+        st = getattr(self, "_stream_state", None)
+        host_norm = bool(self.tracking_config.get("host_normalize", False))
+        if st is None or st["device"] != dev or st["host_norm"] != host_norm:
+            shape, dtype = ((1, 3, 256, 256), torch.float32) if host_norm else ((1, 256, 256, 3), torch.uint8)
+            st = dict(device=dev, host_norm=host_norm, pin=torch.empty(shape, dtype=dtype).pin_memory(),
+                      dev=torch.empty(shape, dtype=dtype, device=dev),
+                      zf=torch.empty((1, 256, 8, 8), dtype=torch.float32, device=dev),
+                      box_pin=torch.empty((1, 48), dtype=torch.uint8).pin_memory(),
+                      graph=None, boxes=None, handle=None, zf_src=None, calls=0)
+            self._stream_state = st
+        if host_norm:
+            np.copyto(st["pin"].numpy(), np.transpose(image_ops.normalize(search_crop[:, :, :3]), (2, 0, 1))[None])
+        else:
+            np.copyto(st["pin"].numpy(), search_crop[None, :, :, :3])
+        st["dev"].copy_(st["pin"], non_blocking=True)
+        if st["zf_src"] is not self._template_features:  # new template (initialize / reset): refresh the static copy
+            st["zf"].copy_(self._template_features)
+            st["zf_src"] = self._template_features
+        use_graph = self.tracking_config.get("cuda_graph", True)
+        handle = getattr(self.net, "_handle", None)
+        if use_graph and st["graph"] is not None and st["handle"] is not handle:
+            st["graph"], st["calls"] = None, 0  # weights were re-packed: the captured pointers are stale
+        if use_graph and st["graph"] is None and st["calls"] >= 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["boxes"] = self.net.track_boxes(st["dev"], st["zf"])
+                st["graph"], st["handle"] = g, getattr(self.net, "_handle", None)
+            except Exception:  # capture unsupported in this context: stay eager
+                self.tracking_config["cuda_graph"] = False
+                torch.cuda.synchronize(dev)
+        if use_graph and st["graph"] is not None and self.tracking_config.get("cuda_graph", True):
+            st["graph"].replay()
+            boxes = st["boxes"]
+        else:
+            boxes = self.net.track_boxes(st["dev"], st["zf"])
+        st["calls"] += 1
+        st["box_pin"].copy_(boxes, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        from . import _lib
+
+        return st["box_pin"].numpy().view(_lib.BOX_DTYPE).reshape(-1)[0].copy()
 
     # -- reference-shaped post-processing on a maps dictionary (used for the optional smoothing) --
     def _postprocess(self, track_result: Dict[str, torch.Tensor]) -> Tuple[np.ndarray, float]:
