@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--corr", default=None, help="correlation kernel implementation: ffma | tcgen05")
     ap.add_argument("--pw", default=None, help="1x1-conv implementation: ffma | tcgen05")
     ap.add_argument("--dw", default=None, help="depthwise implementation: pixel | strip | roll | auto")
+    ap.add_argument("--dw-wide", type=int, default=None)
     ap.add_argument("--fuse", type=int, default=None, help="1 = fused pw-expand+dw kernels for the stride-2 blocks")
     ap.add_argument("--early-sub", type=int, default=None, help="sub-batch (frames) of the high-resolution blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,6 +232,8 @@ def main():
         net.set_option("pw", args.pw)
     if args.dw:
         net.set_option("dw", args.dw)
+    if args.dw_wide is not None:
+        net.set_option("dw_wide", str(args.dw_wide))
     if args.fuse is not None:
         net.set_option("fuse", str(args.fuse))
     if args.early_sub is not None:

@@ -62,6 +62,7 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 
 struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
+  int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
@@ -286,7 +287,13 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
     return check_launch("dw_conv_strip_blocked_kernel");
   }
   if (c->opt.dw == 3 && w.k == 5 && stride == 1 && Wo % 8 == 0 && relu && bias) {
-    // 5x5 stride 1: 8 outputs per thread (12 input + 5 weight loads per 40 FMA4 and kernel row)
+    // 5x5 stride 1: wide strips (fewer loads per FMA: the kernel is bound by L1 wavefronts, not by HBM)
+    if (Wo % 16 == 0 && c->opt.dw_wide) {
+      const long long total = (long long)B * H * (Wo / 16) * C4;
+      dw_conv_strip_kernel<5, 1, 16, true, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(i4, w4, b4, o4, B, H, W,
+                                                                                               C4);
+      return check_launch("dw_conv_strip_kernel<5,1,16>");
+    }
     const long long total = (long long)B * H * (Wo / 8) * C4;
     dw_conv_strip_kernel<5, 1, 8, true, true><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
         i4, w4, b4, o4, B, H, W, C4);
@@ -1032,6 +1039,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "dw_wide")) {
+    o.dw_wide = atoi(value) != 0;
+    return 0;
+  }
   if (!strcmp(key, "fuse")) {
     o.fuse = atoi(value) != 0;
     return 0;

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) dw_conv_nhwc_kernel(const float4* __restr
 // Requires Wo % TX == 0.
 // ------------------------------------------------------------------------------------------
 template <int K, int S, int TX, bool RELU, bool BIAS>
-__global__ void __launch_bounds__(256) dw_conv_strip_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
+__global__ void __launch_bounds__(TX >= 16 ? 128 : 256) dw_conv_strip_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
                                                             const float4* __restrict__ bias, float4* __restrict__ out,
                                                             int B, int H, int W, int C4) {
   const int Ho = H / S, Wo = W / S;

@@ -475,6 +475,51 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
       const float* sb = sbias + acc * 128;
+      if (!p.R && !p.split_acc) {
+        // short-K layers (wide, epilogue-bound): 32 columns per TMEM round trip, single accumulator
+        for (int g = hsel * 32; g < p.NT; g += 64) {
+          uint32_t r32[32];
+          const bool second = g + 16 < p.NT;  // NT is a multiple of 16: the upper half may not exist
+          if (second) {
+            tmem_ld_32x32(taddr + g, r32);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x16(taddr + g, r16);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r32[e] = r16[e];
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !second) break;
+            float4* stg = reinterpret_cast<float4*>(epi_stage + (ew * 2 + buf) * 2048);
+            tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(sb + g + half * 16 + 4 * j);
+              float4 o = make_float4(__uint_as_float(r32[half * 16 + 4 * j]) + b.x,
+                                     __uint_as_float(r32[half * 16 + 4 * j + 1]) + b.y,
+                                     __uint_as_float(r32[half * 16 + 4 * j + 2]) + b.z,
+                                     __uint_as_float(r32[half * 16 + 4 * j + 3]) + b.w);
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stg, n0 + g + half * 16, mt * 128 + q * 32);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+        }
+      } else
       for (int g = hsel * 16; g < p.NT; g += 32) {
         uint32_t r[16], rs[16];
         tmem_ld_32x16(taddr + g, r);
@@ -593,11 +638,11 @@ struct TsParams {
   float* C;
   int ldr, ldc;
   int M, N, NT, num_n_tiles, num_chunks, relu;
-  int a_slots, w_slots, w_slot_bytes, acc_sets, tmem_cols;
+  int a_slots, w_slots, w_slot_bytes, acc_sets, tmem_cols, ta_slots;
   int tiles_per_group, group_mod, group_rows;  // B-matrix selection (0 tiles_per_group = single shared B)
 };
 
-constexpr int kTsThreads = 320;
+constexpr int kTsThreads = 448;  // producer, MMA, 8 convert warps, 4 epilogue warps
 constexpr int kTsASlotBytes = 128 * 128;
 
 __global__ void __launch_bounds__(kTsThreads, 1)
@@ -612,11 +657,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* a_empty = bars + 8;            // [8] convert warps have read the slot (count 4)
   uint64_t* w_full = bars + 16;            // [8] TMA landed W hi + lo
   uint64_t* w_empty = bars + 24;           // [8] MMAs that read the slot completed (commit)
-  uint64_t* ta_full = bars + 32;           // [2] (hi, lo) written to the TMEM A slot (count 4)
-  uint64_t* ta_empty = bars + 34;          // [2] MMAs that read the TMEM A slot completed (commit)
-  uint64_t* acc_full = bars + 36;          // [2]
-  uint64_t* acc_empty = bars + 38;         // [2] (count 4)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  uint64_t* ta_full = bars + 32;           // [4] (hi, lo) written to the TMEM A slot (count 4)
+  uint64_t* ta_empty = bars + 36;          // [4] MMAs that read the TMEM A slot completed (commit)
+  uint64_t* acc_full = bars + 40;          // [2]
+  uint64_t* acc_empty = bars + 42;         // [2] (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 512;  // 4 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -636,13 +681,15 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 64) {
     for (int s = 0; s < 8; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 4);
+      mbar_init(&a_empty[s], 8);
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&ta_full[a], 4);
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(&ta_full[a], 8);
       mbar_init(&ta_empty[a], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 4);
     }
@@ -652,7 +699,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_col0 = 128;  // accumulators start after the two A slots
+  const uint32_t acc_col0 = p.ta_slots * 64;  // accumulators start after the TMEM A slots
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -703,8 +750,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_commit(&ta_empty[ta]);
           tc_commit(&w_empty[sw]);
           if (++sw == p.w_slots) { sw = 0; pw ^= 1; }
-          ta ^= 1;
-          if (ta == 0) pta ^= 1;
+          if (++ta == p.ta_slots) { ta = 0; pta ^= 1; }
         }
         tc_commit(&acc_full[acc]);
         if (p.acc_sets == 2) {
@@ -715,9 +761,11 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ============================ convert: smem fp32 -> TMEM (hi, lo) =======================
+    // 8 warps: two per TMEM lane quadrant, each converting 16 of the 32 channels of its rows
     const int q = warp & 3;            // TMEM lane quadrant of this warp
+    const int hh = (warp - 2) >> 2;    // which 16-channel half of the chunk
     const int row = q * 32 + lane;     // tile row handled by this thread (= TMEM lane)
     int sa = 0, ta = 0;
     uint32_t pa = 0, pta = 0;
@@ -728,8 +776,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const float4* arow = reinterpret_cast<const float4*>(a_ring + sa * kTsASlotBytes + row * 128);
         const uint32_t tdst = tmem_base + ta * 64 + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // 16 channels at a time: 4 swizzled 16-byte chunks of the row
+        {
+          const int h = hh;  // 16 channels: 4 swizzled 16-byte chunks of the row
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -751,8 +799,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive(&ta_full[ta]);
         }
         if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
-        ta ^= 1;
-        if (ta == 0) pta ^= 1;
+        if (++ta == p.ta_slots) { ta = 0; pta ^= 1; }
       }
     }
   } else {
@@ -864,8 +911,10 @@ inline int launch_gemm_ts(cudaStream_t s, const float* A, int lda, const float* 
   p.num_chunks = (K + 31) / 32;
   p.relu = relu;
   p.acc_sets = (128 + 4 * p.NT <= 512) ? 2 : 1;
+  p.ta_slots = (256 + p.acc_sets * 2 * p.NT <= 512) ? 4 : 2;
+  if (const char* e = getenv("FEAR_TS_TASLOTS")) p.ta_slots = atoi(e) == 4 && 256 + p.acc_sets * 2 * p.NT <= 512 ? 4 : 2;
   int cols = 32;
-  while (cols < 128 + p.acc_sets * 2 * p.NT) cols <<= 1;
+  while (cols < p.ta_slots * 64 + p.acc_sets * 2 * p.NT) cols <<= 1;
   p.tmem_cols = cols;
   p.w_slot_bytes = 2 * p.NT * 128;
   // A (activations, HBM latency) gets the deep ring; B (weights / templates, mostly L2 hits) needs few slots
