@@ -217,7 +217,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version at VERSION/INFO)
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"  # NCCL's banner / logs go to stderr: stdout is the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B, total = args.batch, args.batch * world
 
