@@ -57,7 +57,7 @@ enum Stage {
 static const char* kStageNames[ST_COUNT] = {"stem",    "backbone_pw", "backbone_dw", "neck",   "head_dw",
                                             "head_pw", "corr",        "pred",        "decode", "layout"};
 
-enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2 };  // CUDA cores | tcgen05 A-from-smem | tcgen05 A-from-TMEM
+enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2, IMPL_TC2 = 3 };  // CUDA cores | tcgen05 A-from-smem | tcgen05 A-from-TMEM
 
 struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
@@ -401,7 +401,20 @@ static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const
     if (r) return set_err(r, "tcgen05 (TS) corr launch failed (%d)", r);
     return check_launch("tc::gemm_ts(corr)");
   }
-  if (corr_impl == IMPL_TC || corr_impl == IMPL_TS) {
+  if (corr_impl == IMPL_TC2 && zth && ztl) {
+    {
+      LaunchScope scope(c, ST_LAYOUT, s);  // template features -> tf32 (hi, lo) planes
+      const long long n4 = (long long)Bz * kCorrC * kFeatC / 4;
+      tc::split_hi_lo_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
+          reinterpret_cast<const float4*>(zt), reinterpret_cast<float4*>(zth), reinterpret_cast<float4*>(ztl), n4);
+      FEAR_TRY(check_launch("split_hi_lo_kernel"));
+    }
+    LaunchScope scope(c, ST_CORR, s);
+    int r = tc::launch_corr2(s, zth, ztl, Bz, cat, B, groups);
+    if (r) return set_err(r, "tcgen05 (v2) corr launch failed (%d)", r);
+    return check_launch("tc::corr2");
+  }
+  if (corr_impl == IMPL_TC || corr_impl == IMPL_TS || corr_impl == IMPL_TC2) {
     LaunchScope scope(c, ST_CORR, s);
     int r = tc::launch_corr(s, zt, Bz, cat, B, groups);
     if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
@@ -941,7 +954,7 @@ extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B
   if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   float *zth = nullptr, *ztl = nullptr;
-  if (effective(g_default_options.corr) == IMPL_TS) {
+  if (effective(g_default_options.corr) == IMPL_TS || effective(g_default_options.corr) == IMPL_TC2) {
     const size_t need = 2 * (size_t)Bz * kCorrC * kFeatC;
     FEAR_TRY(ensure_scratch2(need));
     zth = g_scratch2;
@@ -1065,6 +1078,7 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
   else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;
   else if (!strcmp(value, "tcgen05ts")) impl = IMPL_TS;
+  else if (!strcmp(value, "tcgen05v2")) impl = IMPL_TC2;
   else if (!strcmp(value, "auto")) impl = -1;
   else return set_err(FEAR_EINVAL, "unknown implementation '%s' (auto | ffma | tcgen05 | tcgen05ts)", value);
   if (impl > IMPL_FFMA && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");

@@ -250,6 +250,232 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// corr_tc2_kernel -- correlation with DECOUPLED landing and operand rings.
+//
+// The ablation of corr_tc_kernel (profiles/r1_corr_ablation.txt) showed its 4-stage ring is latency bound: a
+// stage is held from the TMA issue until the MMAs that read it complete, so only part of the 192 KB of smem is
+// ever "in flight" towards HBM.  Here the TMA lands raw x tiles in a deep ring of pure landing buffers
+// (7 x 16 KB); the split warps copy each tile into a 2-slot operand ring as (hi, lo) and release the landing
+// slot at once; the tensor core reads only the operand ring.  The template tiles come pre-split (hi / lo planes
+// produced once per template by split_hi_lo_kernel) through their own 2-slot ring fed by a second producer warp,
+// so neither ring can stall the other.  Everything else (TMEM accumulators, epilogue) is as in corr_tc_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kC2Landing = 3;   // raw landing slots (TMA in flight)
+constexpr int kC2Ops = 3;       // (hi, lo) operand slots between the split warps and the tensor core
+constexpr int kC2B = 4;         // template (hi, lo) tile slots
+constexpr int kC2Threads = 480;  // A producer, MMA, 8 split warps, 4 epilogue warps, B producer
+constexpr int kC2SmemBytes = kC2Landing * kCorrABytes + kC2Ops * 2 * kCorrABytes + kC2B * 2 * kCorrBBytes + 1024 /*align*/ +
+                             512 /*barriers*/ + 8192 /*epilogue*/;
+
+__global__ void __launch_bounds__(kC2Threads, 1)
+corr_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                const __grid_constant__ CUtensorMap tmBl, float* __restrict__ cat, int num_frames, int z_mod) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* landing = smem;                                   // [7][16 KB] raw x tiles
+  uint8_t* opring = landing + kC2Landing * kCorrABytes;      // [2][hi 16 KB | lo 16 KB]
+  uint8_t* bring = opring + kC2Ops * 2 * kCorrABytes;        // [2][hi 8 KB | lo 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + kC2B * 2 * kCorrBBytes);
+  uint64_t* land_full = bars;            // [7]
+  uint64_t* land_empty = bars + 8;       // [7] count 8 (split warps)
+  uint64_t* op_full = bars + 16;         // [kC2Ops] count 8
+  uint64_t* op_empty = bars + 24;        // [kC2Ops] commit
+  uint64_t* b_full = bars + 32;          // [kC2B]
+  uint64_t* b_empty = bars + 40;         // [kC2B] commit
+  uint64_t* acc_full = bars + 48;        // [2]
+  uint64_t* acc_empty = bars + 50;       // [2] count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = num_frames * 2;
+  constexpr int kChunks = 256 / kCorrChunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmBh);
+    prefetch_tmap(&tmBl);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kCorrTmemCols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x == 64) {
+    for (int s = 0; s < kC2Landing; ++s) {
+      mbar_init(&land_full[s], 1);
+      mbar_init(&land_empty[s], 8);
+    }
+    for (int a = 0; a < kC2Ops; ++a) {
+      mbar_init(&op_full[a], 8);
+      mbar_init(&op_empty[a], 1);
+    }
+    for (int a = 0; a < kC2B; ++a) {
+      mbar_init(&b_full[a], 1);
+      mbar_init(&b_empty[a], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- x producer: keeps up to 7 raw tiles (112 KB) in flight -------------------------------------
+    if (lane == 0) {
+      int sl = 0;
+      uint32_t pl = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int arow = (t >> 1) * 256 + (t & 1) * 128;
+        for (int c = 0; c < kChunks; ++c) {
+          mbar_wait(&land_empty[sl], pl ^ 1);
+          mbar_arrive_expect_tx(&land_full[sl], kCorrABytes);
+          tma_load_2d(landing + sl * kCorrABytes, &tmA, &land_full[sl], c * kCorrChunk, arow);
+          if (++sl == kC2Landing) { sl = 0; pl ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ---- template producer: pre-split (hi, lo) tiles, L2 resident -----------------------------------
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int frame = t >> 1;
+        const int brow = z_mod ? (frame % z_mod) * 64 : 0;
+        for (int c = 0; c < kChunks; ++c) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          mbar_arrive_expect_tx(&b_full[sb], 2 * kCorrBBytes);
+          tma_load_2d(bring + sb * 2 * kCorrBBytes, &tmBh, &b_full[sb], c * kCorrChunk, brow);
+          tma_load_2d(bring + sb * 2 * kCorrBBytes + kCorrBBytes, &tmBl, &b_full[sb], c * kCorrChunk, brow);
+          if (++sb == kC2B) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer -----------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      int so = 0, sb = 0, acc = 0;
+      uint32_t po = 0, pb = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 128;
+        for (int c = 0; c < kChunks; ++c) {
+          mbar_wait(&op_full[so], po);
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(opring + so * 2 * kCorrABytes), al = ah + kCorrABytes;
+          const uint32_t bh = smem_u32(bring + sb * 2 * kCorrBBytes), bl = bh + kCorrBBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
+            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
+            mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
+            mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
+          }
+          tc_commit(&op_empty[so]);
+          tc_commit(&b_empty[sb]);
+          if (++so == kC2Ops) { so = 0; po ^= 1; }
+          if (++sb == kC2B) { sb = 0; pb ^= 1; }
+        }
+        tc_commit(&acc_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 10) {
+    // ---- split: landing slot -> operand slot (hi copy + lo), landing slot released immediately -----------
+    const int ts = threadIdx.x - 64;
+    int sl = 0, so = 0;
+    uint32_t pl = 0, po = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int c = 0; c < kChunks; ++c) {
+        mbar_wait(&land_full[sl], pl);
+        mbar_wait(&op_empty[so], po ^ 1);
+        const float4* src = reinterpret_cast<const float4*>(landing + sl * kCorrABytes);
+        float4* dh = reinterpret_cast<float4*>(opring + so * 2 * kCorrABytes);
+        float4* dl = reinterpret_cast<float4*>(opring + so * 2 * kCorrABytes + kCorrABytes);
+#pragma unroll
+        for (int i = 0; i < kCorrABytes / 16 / 256; ++i) {
+          const float4 v = src[ts + i * 256];
+          float4 h, l;
+          split_tf32_trunc(v.x, h.x, l.x);
+          split_tf32_trunc(v.y, h.y, l.y);
+          split_tf32_trunc(v.z, h.z, l.z);
+          split_tf32_trunc(v.w, h.w, l.w);
+          dh[ts + i * 256] = v;  // raw word = hi operand (kind::tf32 ignores the low 13 bits)
+          dl[ts + i * 256] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&land_empty[sl]);
+          mbar_arrive(&op_full[so]);
+        }
+        if (++sl == kC2Landing) { sl = 0; pl ^= 1; }
+        if (++so == kC2Ops) { so = 0; po ^= 1; }
+      }
+    }
+  } else if (warp < 14) {
+    // ---- epilogue (as in corr_tc_kernel) -----------------------------------------------------------------
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int frame = t >> 1, half = t & 1;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16);
+      const long long row0 = (long long)frame * 256 + half * 128 + q * 32;
+#pragma unroll
+      for (int g = 0; g < 64; g += 16) {
+        uint32_t m[16], sm[16];
+        tmem_ld_32x16(taddr + g, m);
+        tmem_ld_32x16(taddr + 64 + g, sm);
+        tmem_ld_wait();
+        if (g == 48) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
+              make_float4(__uint_as_float(m[4 * j]) + __uint_as_float(sm[4 * j]),
+                          __uint_as_float(m[4 * j + 1]) + __uint_as_float(sm[4 * j + 1]),
+                          __uint_as_float(m[4 * j + 2]) + __uint_as_float(sm[4 * j + 2]),
+                          __uint_as_float(m[4 * j + 3]) + __uint_as_float(sm[4 * j + 3]));
+        __syncwarp();
+        const int j = lane & 3;
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          const int rl = rb * 8 + (lane >> 2);
+          *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
+        }
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kCorrTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 inline int init_pw();
@@ -975,12 +1201,30 @@ inline int pw_tile_n(int N) {
   return 0;
 }
 
+// z_hi / z_lo: tf32 split planes of zt (split_hi_lo_kernel), [Bz*64][256] each.
+inline int launch_corr2(cudaStream_t s, const float* z_hi, const float* z_lo, int Bz, float* cat, int B, int groups) {
+  if (!g_tc_ready) return -20;
+  CUtensorMap tmA, tmBh, tmBl;
+  const int frames = B * groups;
+  int r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
+  if (r) return r;
+  r = make_tmap_2d(&tmBh, z_hi, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
+  if (r) return r;
+  r = make_tmap_2d(&tmBl, z_lo, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
+  if (r) return r;
+  const int tiles = frames * 2;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  corr_tc2_kernel<<<grid, kC2Threads, kC2SmemBytes, s>>>(tmA, tmBh, tmBl, cat, frames, Bz == 1 ? 0 : B);
+  return 0;
+}
+
 inline bool pw_supported(int cin, int cout) {
   return g_tc_ready && cin % 8 == 0 && cout % 8 == 0 && pw_tile_n(cout) != 0;
 }
 
 inline int init_pw() {
-  if (cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+  if (cudaFuncSetAttribute(corr_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
     cudaGetLastError();
     return -1;
