@@ -116,6 +116,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      constexpr uint32_t idesc2 = umma_idesc_tf32(128, 128);  // B' = [z_hi ; z_lo] stacked: 128 rows
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -133,10 +134,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
             // so the (truncating) tensor-core adder rounds the big sum 3x less often
-            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            if (!(exp_mode & 2)) {
-              mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
-              mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
+            if (exp_mode & 2) {
+              mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
+            } else {
+              // the hi and lo template tiles are adjacent in smem, so ONE N=128 MMA yields [x_hi*z_hi | x_hi*z_lo]
+              // in the adjacent (main | correction) accumulators and x_hi is read from smem once, not twice
+              mma_tf32_ss(d, dah, dbh, idesc2, (c | j) != 0);
+              mma_tf32_ss(d + 64, dal, dbh, idesc, 1);
             }
           }
           tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
@@ -618,6 +622,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, p.NT);
+      const uint32_t idesc2 = umma_idesc_tf32(128, 2 * p.NT);  // stacked [W_hi ; W_lo] (NT <= 128)
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -635,10 +640,16 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             // short K (<= 2 chunks): a handful of accumulations, the truncating adder is harmless and a single
             // accumulator halves the TMEM read (64 B/clk/SM) that dominates the epilogue of the wide layers
-            const uint32_t dc = p.split_acc ? d + p.NT : d;
-            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(dc, dal, dbh, idesc, p.split_acc ? ((c | j) != 0) : 1);
-            mma_tf32_ss(dc, dah, dbl, idesc, 1);
+            if (p.split_acc) {
+              // W_hi and W_lo tiles are adjacent in smem: one N = 2*NT MMA gives [a_hi*w_hi | a_hi*w_lo] in the adjacent
+              // (main | correction) accumulators, so the A_hi tile is read from shared memory once instead of twice
+              mma_tf32_ss(d, dah, dbh, idesc2, (c | j) != 0);
+              mma_tf32_ss(d + p.NT, dal, dbh, idesc, 1);
+            } else {
+              mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
+              mma_tf32_ss(d, dal, dbh, idesc, 1);
+              mma_tf32_ss(d, dah, dbl, idesc, 1);
+            }
           }
           tc_commit(&empty[stage]);
           if (++stage == S) {
