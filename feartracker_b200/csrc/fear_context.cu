@@ -13,6 +13,7 @@
 #include "arch.h"
 #include "kernels_ffma.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_dw_tma.cuh"
 
 using namespace fear;
 
@@ -224,6 +225,19 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   float4* o4 = reinterpret_cast<float4*>(out);
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
+  // TMA-fed shared-memory pipeline (kernels_dw_tma.cuh): stride 1, maps that are multiples of 16x16
+  if (c->opt.dw == 6 && tc::available() && stride == 1 && w.c >= 24) {
+    int r = 1;
+    const int sms = tc::g_num_sms;
+    if (w.k == 5 && relu && bias)
+      r = tc::launch_dw_tma_t<5, 1, 16, 16, 8, 2, 4, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
+    else if (w.k == 3 && relu && bias)
+      r = tc::launch_dw_tma_t<3, 1, 16, 16, 8, 2, 5, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
+    else if (w.k == 3 && !relu && !bias)
+      r = tc::launch_dw_tma_t<3, 1, 16, 16, 8, 2, 5, false, false>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
+    if (r < 0) return set_err(FEAR_EINVAL, "TMA depthwise launch failed (%d)", r);
+    if (r == 0) return check_launch("tc::dw_tma_kernel");
+  }
   // shared-memory tiled kernel: stride 1, maps that are multiples of 16x16, channels in 32-slabs
   const bool want_tile = c->opt.dw == 4 && stride == 1 && H % 16 == 0 && W % 16 == 0 &&
                          C4 % 8 == 0 && ((relu && bias) || (!relu && !bias));
@@ -1071,7 +1085,8 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, register strip otherwise
     else if (!strcmp(value, "tile")) o.dw = 4;
     else if (!strcmp(value, "blocked")) o.dw = 5;
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | blocked | auto)", value);
+    else if (!strcmp(value, "tma")) o.dw = 6;
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | blocked | tma | auto)", value);
     return 0;
   }
   int impl;

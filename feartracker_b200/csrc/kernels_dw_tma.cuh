@@ -1,0 +1,239 @@
+// TMA-fed depthwise convolution (channels-last fp32), sm_100a.
+//
+// The register-strip kernels in kernels_ffma.cuh fetch every input pixel straight from global memory; ncu shows
+// them latency-bound on the 5x5 layers (2 TB/s of DRAM traffic, ~50 % L1 hit rate, 4x the algorithmic bytes
+// through L2).  Here a persistent CTA streams (TH x TW pixels) x 32-channel tiles through a shared-memory ring:
+//
+//   producer      : (first warp of each group, one lane) one 4-D cp.async.bulk.tensor per tile -- box = [IH][IW][32 ch], IH = (TH-1)*S+K -- whose
+//                   out-of-image halo is zero-filled by the TMA unit (= the conv's zero padding, no branches),
+//                   plus the [K*K][32] weight slab and the 32 biases of that channel block, all on one mbarrier
+//   consumer warps: two groups of four warps take alternate tiles; lane = (channel group of 4, tile position); each thread produces a TY x TX block of
+//                   output pixels for its 4 channels from LDS.128 reads (a quarter warp reads 128 contiguous
+//                   bytes: conflict free), FMA order (ky, kx ascending from the bias) identical to the other
+//                   depthwise kernels so the results are bit-identical, then stores float4s (128 B / pixel).
+//
+// Every input byte is read from HBM/L2 once per tile (halo overlap only), every output byte written once.
+#pragma once
+#include "tc_common.cuh"
+
+namespace fear {
+namespace tc {
+
+struct DwTmaParams {
+  float* out;  // [B][Ho][Wo][C]
+  int C4;      // C / 4
+  int Ho, Wo;
+  int tiles_x, tiles_y, cblocks;
+  int num_tiles;
+  int exp_mode;  // PERF EXPERIMENTS ONLY (wrong results): 1 = no compute, 2 = no TMA waits, 3 = no stores
+};
+
+constexpr int kDwCB = 32;           // channels per tile
+constexpr int kDwGroupWarps = 4;     // consumer warps working on one tile
+constexpr int kDwGroups = 2;         // consumer groups; group g takes the tiles with (iteration % kDwGroups) == g
+constexpr int kDwConsumerWarps = kDwGroupWarps * kDwGroups;
+constexpr int kDwThreads = kDwConsumerWarps * 32;  // 8 warps = 2 per SM sub-partition: the full 255-register budget
+
+template <int K, int S, int TH, int TW>
+struct DwTile {
+  static constexpr int IH = (TH - 1) * S + K;
+  static constexpr int IW = (TW - 1) * S + K;
+  static constexpr int kInBytes = IH * IW * kDwCB * 4;
+  static constexpr int kWBytes = K * K * kDwCB * 4;
+  static constexpr int kBiasBytes = kDwCB * 4;
+  static constexpr int kStageBytes = kInBytes + kWBytes + kBiasBytes;  // all multiples of 128
+};
+
+template <int K, int S, int TH, int TW, int STAGES>
+constexpr int dw_tma_smem_bytes() {
+  return STAGES * DwTile<K, S, TH, TW>::kStageBytes + 2 * STAGES * 8 + 128;
+}
+
+template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, bool RELU, bool BIAS>
+__global__ void __launch_bounds__(kDwThreads, 1)
+dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+              const __grid_constant__ CUtensorMap tmBias, const DwTmaParams p) {
+  using T = DwTile<K, S, TH, TW>;
+  constexpr int P = K / 2;
+  constexpr int IW = T::IW;
+  constexpr int NIN = (TX - 1) * S + K;  // input columns feeding TX outputs
+  constexpr int NR = (TY - 1) * S + K;   // input rows feeding TY outputs
+  constexpr int PX = TW / TX, PY = TH / TY;
+  constexpr int NPOS = PX * PY;
+  static_assert(TW % TX == 0 && TH % TY == 0, "tile must be a multiple of the thread block");
+
+  extern __shared__ uint8_t dw_smem_raw[];
+  // (offset arithmetic on the __shared__ array itself keeps the address space visible to the compiler: LDS, not LD)
+  uint8_t* smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * T::kStageBytes);
+  uint64_t* empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kDwGroupWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // One 4-D box (+ weight slab + biases) per tile, all completing on full[stage].
+  auto issue_tile = [&](int tile, int stage) {
+    if (p.exp_mode == 2) return;
+    const int cb = tile % p.cblocks;
+    int rest = tile / p.cblocks;
+    const int tx = rest % p.tiles_x;
+    rest /= p.tiles_x;
+    const int ty = rest % p.tiles_y;
+    const int b = rest / p.tiles_y;
+    uint8_t* st = smem + stage * T::kStageBytes;
+    mbar_arrive_expect_tx(&full[stage], T::kInBytes + T::kWBytes + (BIAS ? T::kBiasBytes : 0));
+    tma_load_4d(st, &tmIn, &full[stage], cb * kDwCB, tx * TW * S - P, ty * TH * S - P, b);
+    tma_load_2d(st + T::kInBytes, &tmW, &full[stage], cb * kDwCB, 0);
+    if (BIAS) tma_load_2d(st + T::kInBytes + T::kWBytes, &tmBias, &full[stage], cb * kDwCB, 0);
+  };
+  if (threadIdx.x == 0) {  // prologue: fill the ring
+    for (int i = 0; i < STAGES; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      if (tile < p.num_tiles) issue_tile(tile, i);
+    }
+  }
+
+  // ---------------- consumers ----------------
+  const int cg = lane & 7;  // channel group (float4) inside the 32-channel block
+  const int group = warp / kDwGroupWarps, gwarp = warp % kDwGroupWarps;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    if (it % kDwGroups != group) continue;
+    const int s = it % STAGES;
+    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+    const int cb = tile % p.cblocks;
+    int rest = tile / p.cblocks;
+    const int tx = rest % p.tiles_x;
+    rest /= p.tiles_x;
+    const int ty = rest % p.tiles_y;
+    const int b = rest / p.tiles_y;
+    const int c4 = cb * (kDwCB / 4) + cg;
+    if (p.exp_mode != 2) mbar_wait(&full[s], ph);
+    const float4* in4 = reinterpret_cast<const float4*>(smem + s * T::kStageBytes);
+    const float4* w4 = reinterpret_cast<const float4*>(smem + s * T::kStageBytes + T::kInBytes);
+    const float4* b4p = reinterpret_cast<const float4*>(smem + s * T::kStageBytes + T::kInBytes + T::kWBytes);
+
+#pragma unroll 1
+    for (int pos = gwarp * 4 + (lane >> 3); pos < (p.exp_mode == 1 ? 0 : NPOS); pos += kDwGroupWarps * 4) {
+      const int px = pos % PX, py = pos / PX;
+      const int ox_l = px * TX, oy_l = py * TY;
+      float4 acc[TY][TX];
+      const float4 bias4 = BIAS ? b4p[cg] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int y = 0; y < TY; ++y)
+#pragma unroll
+        for (int t = 0; t < TX; ++t) acc[y][t] = bias4;
+      float4 wk[K][K];
+      const float4* base = in4 + ((oy_l * S) * IW + ox_l * S) * (kDwCB / 4) + cg;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        float4 v[NIN];
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) v[i] = base[(r * IW + i) * (kDwCB / 4)];
+        if (r < K) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) wk[r < K ? r : 0][kx] = w4[(r * K + kx) * (kDwCB / 4) + cg];
+        }
+#pragma unroll
+        for (int y = 0; y < TY; ++y) {
+          const int ky = r - y * S;
+          if (ky >= 0 && ky < K) {
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+              const float4 k = wk[(ky >= 0 && ky < K) ? ky : 0][kx];
+#pragma unroll
+              for (int t = 0; t < TX; ++t) {
+                const float4 x = v[t * S + kx];
+                acc[y][t].x = fmaf(x.x, k.x, acc[y][t].x);
+                acc[y][t].y = fmaf(x.y, k.y, acc[y][t].y);
+                acc[y][t].z = fmaf(x.z, k.z, acc[y][t].z);
+                acc[y][t].w = fmaf(x.w, k.w, acc[y][t].w);
+              }
+            }
+          }
+        }
+      }
+      if (c4 < p.C4 && (p.exp_mode != 3 || acc[0][0].x == 123.456f)) {
+        float4* o = reinterpret_cast<float4*>(p.out) +
+                    (((long long)b * p.Ho + ty * TH + oy_l) * p.Wo + tx * TW + ox_l) * p.C4 + c4;
+#pragma unroll
+        for (int y = 0; y < TY; ++y)
+#pragma unroll
+          for (int t = 0; t < TX; ++t) {
+            float4 r4 = acc[y][t];
+            if (RELU) {
+              r4.x = fmaxf(r4.x, 0.f);
+              r4.y = fmaxf(r4.y, 0.f);
+              r4.z = fmaxf(r4.z, 0.f);
+              r4.w = fmaxf(r4.w, 0.f);
+            }
+            o[((long long)y * p.Wo + t) * p.C4] = r4;
+          }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty[s]);
+      if (gwarp == 0) {  // refill this stage with the tile STAGES iterations ahead once the whole group has left it
+        const int next = tile + STAGES * gridDim.x;
+        if (next < p.num_tiles) {
+          if (p.exp_mode != 2) mbar_wait(&empty[s], ph);
+          issue_tile(next, s);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Host launcher.  Returns 0 on launch, 1 when the shape is not covered (caller falls back), < 0 on error.
+template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, bool RELU, bool BIAS>
+inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, const float* bias, float* out, int B, int H,
+                           int W, int C, int num_sms) {
+  using T = DwTile<K, S, TH, TW>;
+  const int Ho = H / S, Wo = W / S;
+  if (Ho % TH || Wo % TW || C % 4) return 1;
+  auto kern = dw_tma_kernel<K, S, TH, TW, TX, TY, STAGES, RELU, BIAS>;
+  constexpr int smem = dw_tma_smem_bytes<K, S, TH, TW, STAGES>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
+    attr_done = true;
+  }
+  CUtensorMap tmIn, tmW, tmB;
+  int r = make_tmap_nhwc(&tmIn, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)C, kDwCB, T::IW, T::IH);
+  if (r) return r;
+  r = make_tmap_2d_plain(&tmW, w, (uint64_t)K * K, (uint64_t)C, K * K, kDwCB);
+  if (r) return r;
+  if (BIAS) {
+    r = make_tmap_2d_plain(&tmB, bias, 1, (uint64_t)C, 1, kDwCB);
+    if (r) return r;
+  } else {
+    tmB = tmW;
+  }
+  DwTmaParams p;
+  p.out = out;
+  p.C4 = C / 4;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.tiles_x = Wo / TW;
+  p.tiles_y = Ho / TH;
+  p.cblocks = (C + kDwCB - 1) / kDwCB;
+  p.num_tiles = B * p.tiles_x * p.tiles_y * p.cblocks;
+  p.exp_mode = 0;
+  if (const char* e = getenv("FEAR_EXP_DW")) p.exp_mode = atoi(e);
+  int grid = num_sms;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  kern<<<grid, kDwThreads, smem, s>>>(tmIn, tmW, tmB, p);
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace fear

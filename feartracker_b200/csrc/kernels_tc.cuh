@@ -48,7 +48,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // exp_mode (PERF EXPERIMENTS ONLY, results wrong): 1 = skip the split arithmetic, 2 = one MMA per K-step,
   // 4 = skip the epilogue stores.  0 in production.
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes);
   uint64_t* full = bars;                       // [stages] TMA landed
   uint64_t* split = bars + kCorrStages;        // [stages] hi/lo tiles ready for the tensor core
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kC2Threads, 1)
 corr_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                 const __grid_constant__ CUtensorMap tmBl, float* __restrict__ cat, int num_frames, int z_mod) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   uint8_t* landing = smem;                                   // [7][16 KB] raw x tiles
   uint8_t* opring = landing + kC2Landing * kCorrABytes;      // [2][hi 16 KB | lo 16 KB]
   uint8_t* bring = opring + kC2Ops * 2 * kCorrABytes;        // [2][hi 8 KB | lo 8 KB]
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC, const PwParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   const int S = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * p.stage_bytes);
   uint64_t* full = bars;
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TsParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + p.a_slots * kTsASlotBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + p.w_slots * p.w_slot_bytes);

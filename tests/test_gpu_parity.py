@@ -229,7 +229,7 @@ def test_free_running_video_trajectory(net):
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
 
 
-@pytest.mark.parametrize("impl", ["strip", "roll", "tile", "blocked"])
+@pytest.mark.parametrize("impl", ["strip", "roll", "tile", "blocked", "tma"])
 def test_depthwise_variants_are_bit_identical(net, impl):
     """The register-strip / rolling-window depthwise kernels accumulate in the same order as the per-pixel one."""
     zt, xt, _, _ = fo.synthetic_crops(2)
