@@ -66,7 +66,8 @@ struct Options {
   int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
-  int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel
+  int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel,
+               // 4 = smem tile, 5 = L1-blocked strip, 6 = TMA pipeline only where it applies (auto also uses it)
 };
 static Options g_default_options;
 static inline int effective(int impl) { return impl >= 0 ? impl : (tc::available() ? IMPL_TC : IMPL_FFMA); }
@@ -226,15 +227,22 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   const bool bias = w.b != nullptr;
   const int Wo = W / stride;
   // TMA-fed shared-memory pipeline (kernels_dw_tma.cuh): stride 1, maps that are multiples of 16x16
-  if (c->opt.dw == 6 && tc::available() && stride == 1 && w.c >= 24) {
+  const bool want_tma = (c->opt.dw == 6 || c->opt.dw == 3) && tc::available();
+  if (want_tma && stride == 2 && w.k == 5 && relu && bias) {
+    // 5x5 stride 2: 8x8 output tiles (19x19 input pixels), 4x1 outputs per thread
+    int r = tc::launch_dw_tma_t<5, 2, 8, 8, 4, 1, 4, 2, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, tc::g_num_sms);
+    if (r < 0) return set_err(FEAR_EINVAL, "TMA depthwise launch failed (%d)", r);
+    if (r == 0) return check_launch("tc::dw_tma_kernel<5,2>");
+  }
+  // TMA-fed shared-memory pipeline (kernels_dw_tma.cuh): stride 1, maps that are multiples of 16x16
+  if (want_tma && stride == 1 && w.c >= 24) {
     int r = 1;
-    const int sms = tc::g_num_sms;
-    if (w.k == 5 && relu && bias)
-      r = tc::launch_dw_tma_t<5, 1, 16, 16, 8, 2, 4, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
-    else if (w.k == 3 && relu && bias)
-      r = tc::launch_dw_tma_t<3, 1, 16, 16, 8, 2, 5, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
-    else if (w.k == 3 && !relu && !bias)
-      r = tc::launch_dw_tma_t<3, 1, 16, 16, 8, 2, 5, false, false>(s, in, w.w, w.b, out, B, H, W, w.c, sms);
+#define DW_TMA(K_, RELU_, BIAS_) \
+  tc::launch_dw_tma_t<K_, 1, 16, 16, 8, 2, 4, 2, RELU_, BIAS_>(s, in, w.w, w.b, out, B, H, W, w.c, tc::g_num_sms)
+    if (w.k == 5 && relu && bias) r = DW_TMA(5, true, true);
+    else if (w.k == 3 && relu && bias) r = DW_TMA(3, true, true);
+    else if (w.k == 3 && !relu && !bias) r = DW_TMA(3, false, false);
+#undef DW_TMA
     if (r < 0) return set_err(FEAR_EINVAL, "TMA depthwise launch failed (%d)", r);
     if (r == 0) return check_launch("tc::dw_tma_kernel");
   }
@@ -1082,7 +1090,7 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     if (!strcmp(value, "pixel")) o.dw = 0;
     else if (!strcmp(value, "strip")) o.dw = 1;
     else if (!strcmp(value, "roll")) o.dw = 2;
-    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: rolling window for 3x3 s1, register strip otherwise
+    else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: TMA pipeline where it applies, else rolling window (3x3 s1) / register strip
     else if (!strcmp(value, "tile")) o.dw = 4;
     else if (!strcmp(value, "blocked")) o.dw = 5;
     else if (!strcmp(value, "tma")) o.dw = 6;

@@ -543,6 +543,7 @@ struct PwParams {
   int ldr, ldc;
   int M, N, NT, num_n_tiles, num_chunks, last_ksteps, relu, stages, stage_bytes, tmem_cols;
   int split_acc;  // 1: hi*hi and the cross terms accumulate separately (long K); 0: one accumulator (K <= 64)
+  int acc_stride; // TMEM columns per accumulator stage: 2*NT (main + correction) or NT
 };
 
 constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
@@ -561,7 +562,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;      // 8 warps x 2 buffers x 2 KB, 512-B aligned
-  float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][128] per accumulator stage
+  float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][256] per accumulator stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_tiles = (p.M + 127) >> 7;
@@ -628,7 +629,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * 2 * p.NT;  // main; + NT = correction accumulator
+        const uint32_t d = tmem_base + acc * p.acc_stride;  // main; + NT = correction accumulator (split_acc)
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&split[stage], phase);
           tc_fence_after();
@@ -706,12 +707,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
       const int n0 = nt * p.NT;
       // bias of this tile's columns -> smem (one slot per accumulator stage); named barrier over the 8 warps
-      if (etid < p.NT) sbias[acc * 128 + etid] = (p.bias && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+      if (etid < p.NT) sbias[acc * 256 + etid] = (p.bias && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
-      const float* sb = sbias + acc * 128;
+      const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
+      const float* sb = sbias + acc * 256;
       if (!p.R && !p.split_acc) {
         // short-K layers (wide, epilogue-bound): 32 columns per TMEM round trip, single accumulator
         for (int g = hsel * 32; g < p.NT; g += 64) {
@@ -849,7 +850,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/driver slack
-constexpr int kPwTailBytes = 1024 /*barriers*/ + 8 * 2 * 2048 /*epilogue staging*/ + 1024 /*bias*/;
+constexpr int kPwTailBytes = 1024 /*barriers*/ + 8 * 2 * 2048 /*epilogue staging*/ + 2048 /*bias*/;
 
 // ------------------------------------------------------------------------------------------
 // gemm_ts_kernel -- second-generation tensor-core GEMM: the activation operand lives in TENSOR MEMORY.
@@ -1203,12 +1204,15 @@ __global__ void split_hi_lo_kernel(const float4* __restrict__ src, float4* __res
   // 227 KB opt-in limit minus static/driver slack
 
 // Output-channel tile for a layer: largest divisor-style tile <= 256 that is a multiple of 16.
-inline int pw_tile_n(int N) {
+// wide = single-chunk layers (K <= 32, one accumulator per stage): tiles up to 256 columns.  Those layers are
+// bound by the per-tile round trips (TMA -> split -> MMA -> epilogue), so fewer, wider tiles win.
+inline int pw_tile_n(int N, bool wide = false) {
   // <= 128 so that 2 buffers x (main + correction) accumulators fit the 512 TMEM columns
+  const int limit = wide ? 256 : 128;
   const int Np = (N + 15) & ~15;  // N = 24 -> 32 (weight rows >= N are zero-filled by TMA)
-  if (Np <= 128) return Np;
+  if (Np <= limit) return Np;
   for (int parts = 2; parts <= 8; ++parts)
-    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 128) return Np / parts;
+    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= limit) return Np / parts;
   return 0;
 }
 
@@ -1255,19 +1259,20 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.ldc = ldc;
   p.M = M;
   p.N = N;
-  p.NT = pw_tile_n(N);
+  p.num_chunks = (K + 31) / 32;
+  p.NT = pw_tile_n(N, p.num_chunks == 1 && !getenv("FEAR_PW_NARROW"));
   if (!p.NT) return -21;
   p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
-  p.num_chunks = (K + 31) / 32;
   p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
   p.split_acc = p.num_chunks > 2;
+  p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
   p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
   p.stages = (kPwMaxSmem - 1024 - kPwTailBytes) / p.stage_bytes;
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return -22;
   int cols = 32;
-  while (cols < 4 * p.NT) cols <<= 1;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap tmA, tmWh, tmWl;
   int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
