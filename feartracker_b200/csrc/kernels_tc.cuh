@@ -703,12 +703,27 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    // Bias of a tile's columns lives in smem, one slot per accumulator stage.  The global load is issued one tile
+    // ahead (its L2 latency used to sit on the per-tile critical path); layers with a single N tile load it once.
+    const bool fixed_bias = p.num_n_tiles == 1;
+    auto load_bias = [&](int tile) -> float {
+      const int col = (tile % p.num_n_tiles) * p.NT + etid;
+      return (p.bias && etid < p.NT && col < p.N) ? __ldg(p.bias + col) : 0.f;
+    };
+    float bias_next = blockIdx.x < num_tiles ? load_bias(blockIdx.x) : 0.f;
+    if (fixed_bias) {
+      sbias[etid] = bias_next;
+      sbias[256 + etid] = bias_next;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
       const int n0 = nt * p.NT;
-      // bias of this tile's columns -> smem (one slot per accumulator stage); named barrier over the 8 warps
-      if (etid < p.NT) sbias[acc * 256 + etid] = (p.bias && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!fixed_bias) {
+        sbias[acc * 256 + etid] = bias_next;
+        if (t + (int)gridDim.x < num_tiles) bias_next = load_bias(t + gridDim.x);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // named barrier over the 8 epilogue warps
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
