@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--dw", default=None, help="depthwise implementation: pixel | strip | roll | auto")
     ap.add_argument("--dw-wide", type=int, default=None)
     ap.add_argument("--fuse", type=int, default=None, help="1 = fused pw-expand+dw kernels for the stride-2 blocks")
+    ap.add_argument("--fuse-stem", type=int, default=None, help="0 = separate stem / xif1_0 kernels")
     ap.add_argument("--early-sub", type=int, default=None, help="sub-batch (frames) of the high-resolution blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -236,6 +237,8 @@ def main():
         net.set_option("dw_wide", str(args.dw_wide))
     if args.fuse is not None:
         net.set_option("fuse", str(args.fuse))
+    if args.fuse_stem is not None:
+        net.set_option("fuse_stem", str(args.fuse_stem))
     if args.early_sub is not None:
         net.set_option("early_sub", str(args.early_sub))
 

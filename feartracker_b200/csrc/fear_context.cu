@@ -14,6 +14,7 @@
 #include "kernels_ffma.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_dw_tma.cuh"
+#include "kernels_stem_fused.cuh"
 
 using namespace fear;
 
@@ -64,6 +65,7 @@ struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
   int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
+  int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel,
@@ -103,6 +105,7 @@ struct EventPair {
 };
 
 struct FearContext {
+  FsWeights fs;  // host copy of the stem + xif1_0 weights, passed by value to stem_xif1_fused_kernel
   int device = 0;
   Options opt;
   float* d_weights = nullptr;
@@ -514,7 +517,35 @@ static int run_backbone(FearContext* c, cudaStream_t s, const void* img, int B, 
   int h = H / 2, w = W / 2;
   for (int b0 = 0; b0 < B; b0 += sub) {
     const int nb = (B - b0 < sub) ? B - b0 : sub;
-    {
+    // (TMA needs 16-byte aligned image rows and base: W % 16 == 0 covers both layouts)
+    const bool fuse_stem = c->opt.fuse_stem && tc::available() && (H / 2) % kFsTH == 0 && (W / 2) % kFsTW == 0 &&
+                           (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+    if (fuse_stem) {
+      // stem + xif1_0 (dw3x3 -> 1x1 + residual) in one pass over the image: the block output lands in bufX
+      LaunchScope scope(c, ST_STEM, s);
+      static bool attr_done = false;
+      if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
+        attr_done = true;
+      }
+      const unsigned blocks = (unsigned)((long long)nb * ((H / 2) / kFsTH) * ((W / 2) / kFsTW));
+      CUtensorMap tm;
+      if (u8) {
+        const uint8_t* base = static_cast<const uint8_t*>(img) + (long long)b0 * 3 * H * W;
+        int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, base, (uint64_t)3 * W, (uint64_t)H, (uint64_t)nb,
+                                 (uint64_t)3 * W, (uint64_t)3 * W * H, kFsRawPitch, kFsPH, 1);
+        if (r) return set_err(FEAR_EINVAL, "tensor map for the uint8 image failed (%d)", r);
+        stem_xif1_fused_kernel<true><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, imagenet_norm(), c->fs);
+      } else {
+        const float* base = static_cast<const float*>(img) + (long long)b0 * 3 * H * W;
+        int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, (uint64_t)W, (uint64_t)H, (uint64_t)3 * nb,
+                                 (uint64_t)W * 4, (uint64_t)W * H * 4, kFsPP, kFsPH, 3);
+        if (r) return set_err(FEAR_EINVAL, "tensor map for the float image failed (%d)", r);
+        stem_xif1_fused_kernel<false><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, StemNorm(), c->fs);
+      }
+      FEAR_TRY(check_launch("stem_xif1_fused_kernel"));
+    } else {
       LaunchScope scope(c, ST_STEM, s);
       const unsigned blocks = (unsigned)((long long)nb * ((H / 2 + 3) / 4) * ((W / 2 + 31) / 32));
       if (u8)
@@ -527,7 +558,8 @@ static int run_backbone(FearContext* c, cudaStream_t s, const void* img, int B, 
     }
     h = H / 2;
     w = W / 2;
-    FEAR_TRY(run_blocks(c, s, c->bufX, nb, h, w, 0, kEarlyBlocks, blocked ? c->bufS + b0 * per_frame_s : nullptr, &X));
+    FEAR_TRY(run_blocks(c, s, c->bufX, nb, h, w, fuse_stem ? 1 : 0, kEarlyBlocks,
+                        blocked ? c->bufS + b0 * per_frame_s : nullptr, &X));
   }
   if (blocked) X = c->bufS;
   float* out = nullptr;
@@ -743,6 +775,18 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
     cudaFree(c->d_weights);
     delete c;
     return set_err(FEAR_ESTATE, "internal: weight table walk consumed %d of %d tensors", idx, n);
+  }
+  {
+    auto host_of = [&](const float* dptr) { return arena.data() + (dptr - c->d_weights); };
+    const BlockW& b0 = c->blocks[0];
+    memcpy(c->fs.sw, host_of(c->stem_w), sizeof(c->fs.sw));
+    memcpy(c->fs.sb, host_of(c->stem_b), sizeof(c->fs.sb));
+    memcpy(c->fs.dw, host_of(b0.dw.w), sizeof(c->fs.dw));
+    memcpy(c->fs.db, host_of(b0.dw.b), sizeof(c->fs.db));
+    const float* pw = host_of(b0.pwl.w);  // [o][k]
+    for (int o = 0; o < 16; ++o)
+      for (int k = 0; k < 16; ++k) c->fs.pw[k * 16 + o] = pw[o * 16 + k];
+    memcpy(c->fs.pb, host_of(b0.pwl.b), sizeof(c->fs.pb));
   }
   *handle = c;
   int r = fear_reserve(c, 1);
@@ -1074,6 +1118,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "fuse_stem")) {
+    o.fuse_stem = atoi(value) != 0;
+    return 0;
+  }
   if (!strcmp(key, "dw_wide")) {
     o.dw_wide = atoi(value) != 0;
     return 0;

@@ -277,6 +277,21 @@ def test_fused_expand_depthwise_blocks(net, sd64):
         assert e2 < 2e-5, (name, e1, e2)
 
 
+def test_fused_stem_block_is_bit_identical(net):
+    """stem + xif1_0 in one kernel (the default) == the four separate kernels, for float and uint8 inputs."""
+    zt, xt, zu, xu = fo.synthetic_crops(3)
+    zu8 = zu.permute(0, 2, 3, 1).contiguous().cuda()
+    xu8 = xu.permute(0, 2, 3, 1).contiguous().cuda()
+    fused = [net.get_features(zt.cuda()), net.get_features(xt.cuda()), net.get_features(zu8), net.get_features(xu8)]
+    net.set_option("fuse_stem", "0")
+    try:
+        plain = [net.get_features(zt.cuda()), net.get_features(xt.cuda()), net.get_features(zu8), net.get_features(xu8)]
+    finally:
+        net.set_option("fuse_stem", "1")
+    for a, b in zip(fused, plain):
+        assert torch.equal(a, b)
+
+
 def test_uint8_input_path_is_bit_identical(net):
     """Raw uint8 HWC crops normalised inside the stem kernel == float crops normalised on the host."""
     _, _, zu, xu = fo.synthetic_crops(3)
