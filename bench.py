@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--fuse", type=int, default=None, help="1 = fused pw-expand+dw kernels for the stride-2 blocks")
     ap.add_argument("--fuse-stem", type=int, default=None, help="0 = separate stem / xif1_0 kernels")
     ap.add_argument("--early-sub", type=int, default=None, help="sub-batch (frames) of the high-resolution blocks")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra fear_set_option pairs (experiments), e.g. --opt small_const=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -239,6 +241,9 @@ def main():
         net.set_option("fuse", str(args.fuse))
     if args.fuse_stem is not None:
         net.set_option("fuse_stem", str(args.fuse_stem))
+    for kv in args.opt:
+        k, v = kv.split("=", 1)
+        net.set_option(k, v)
     if args.early_sub is not None:
         net.set_option("early_sub", str(args.early_sub))
 

@@ -65,6 +65,7 @@ struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
   int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
+  int small_const = 1;  // 1: tiny 1x1 layers take their weights by value (constant bank) instead of via shared memory
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
   int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
@@ -79,6 +80,8 @@ struct PwW {
   const float* w_hi = nullptr;  // tf32 split of w for the tcgen05 path: w ~= w_hi + w_lo
   const float* w_lo = nullptr;
   const float* b = nullptr;
+  const float* h_w = nullptr;  // host copies (persistent): small layers pass their weights by value
+  const float* h_b = nullptr;
   int cin = 0, cout = 0;
 };
 struct DwW {
@@ -109,6 +112,7 @@ struct FearContext {
   int device = 0;
   Options opt;
   float* d_weights = nullptr;
+  std::vector<float> h_weights;  // host mirror of d_weights (device layout)
   const float *stem_w = nullptr, *stem_b = nullptr;
   BlockW blocks[kNumBlocks];
   PwW neck;
@@ -196,6 +200,23 @@ static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, 
     // streaming layers: one pixel per thread on CUDA cores beats a tensor-core tile pipeline here
     LaunchScope scope(c, stage, s);
     const unsigned blocks = (unsigned)((M + 255) / 256);
+    if (c->opt.small_const && w.h_w && w.h_b) {
+      // weights by value in the constant bank (see pw_small_const_kernel)
+      if (w.cin == 16) {
+        PwSmallWeights<16, 16> pw;
+        for (int o = 0; o < 16; ++o)
+          for (int k = 0; k < 16; ++k) pw.w[k * 16 + o] = w.h_w[o * 16 + k];
+        memcpy(pw.b, w.h_b, sizeof(pw.b));
+        pw_small_const_kernel<16, 16><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
+      } else {
+        PwSmallWeights<24, 24> pw;
+        for (int o = 0; o < 24; ++o)
+          for (int k = 0; k < 24; ++k) pw.w[k * 24 + o] = w.h_w[o * 24 + k];
+        memcpy(pw.b, w.h_b, sizeof(pw.b));
+        pw_small_const_kernel<24, 24><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
+      }
+      return check_launch("pw_small_const_kernel");
+    }
     if (w.cin == 16)
       pw_small_kernel<16, 16><<<blocks, 256, 0, s>>>(A, w.w, w.b, R, C, M, relu);
     else
@@ -738,6 +759,8 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
     w.w_lo = c->d_weights + lo_off[idx];
     w.w = next();
     w.b = next();
+    w.h_w = reinterpret_cast<const float*>((w.w - c->d_weights));  // offsets for now; rebased onto h_weights below
+    w.h_b = reinterpret_cast<const float*>((w.b - c->d_weights));
     w.cin = cin;
     w.cout = cout;
   };
@@ -776,8 +799,26 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
     delete c;
     return set_err(FEAR_ESTATE, "internal: weight table walk consumed %d of %d tensors", idx, n);
   }
+  c->h_weights = std::move(arena);
   {
-    auto host_of = [&](const float* dptr) { return arena.data() + (dptr - c->d_weights); };
+    auto rebase = [&](PwW& w) {
+      w.h_w = c->h_weights.data() + reinterpret_cast<intptr_t>(w.h_w);
+      w.h_b = c->h_weights.data() + reinterpret_cast<intptr_t>(w.h_b);
+    };
+    for (int i = 0; i < kNumBlocks; ++i) {
+      if (kBlocks[i].has_pw()) rebase(c->blocks[i].pw);
+      rebase(c->blocks[i].pwl);
+    }
+    rebase(c->neck);
+    for (int br = 0; br < 2; ++br) {
+      rebase(c->branch[br].enc_pw);
+      rebase(c->branch[br].corr_pw);
+    }
+    for (int t = 0; t < 2; ++t)
+      for (int i = 0; i < 2; ++i) rebase(c->tower[t].pw[i]);
+  }
+  {
+    auto host_of = [&](const float* dptr) { return c->h_weights.data() + (dptr - c->d_weights); };
     const BlockW& b0 = c->blocks[0];
     memcpy(c->fs.sw, host_of(c->stem_w), sizeof(c->fs.sw));
     memcpy(c->fs.sb, host_of(c->stem_b), sizeof(c->fs.sb));
@@ -1118,6 +1159,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "small_const")) {
+    o.small_const = atoi(value) != 0;
+    return 0;
+  }
   if (!strcmp(key, "fuse_stem")) {
     o.fuse_stem = atoi(value) != 0;
     return 0;

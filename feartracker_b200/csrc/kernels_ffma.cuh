@@ -740,6 +740,64 @@ __global__ void __launch_bounds__(256) pw_small_kernel(const float* __restrict__
   }
 }
 
+// Same layer with the weights passed BY VALUE (kernel parameter = constant bank): every FFMA takes its weight as a
+// uniform-register / constant operand instead of a shared-memory broadcast.  An LDS costs one LSU wavefront per
+// 4 bytes even when all lanes read the same address, which made the smem version LSU-bound (CIN*COUT/4 LDS.128
+// per pixel against CIN*COUT FMAs).  Same accumulation order => bit-identical results.
+template <int CIN, int COUT>
+struct PwSmallWeights {
+  float w[CIN * COUT];  // [k][o]
+  float b[COUT];
+};
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) pw_small_const_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                             float* __restrict__ out, long long M, int relu,
+                                                             const __grid_constant__ PwSmallWeights<CIN, COUT> wts) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float xin[CIN];
+  const float4* xp = reinterpret_cast<const float4*>(x + m * CIN);
+#pragma unroll
+  for (int i = 0; i < CIN / 4; ++i) {
+    const float4 v = __ldg(xp + i);
+    xin[4 * i] = v.x;
+    xin[4 * i + 1] = v.y;
+    xin[4 * i + 2] = v.z;
+    xin[4 * i + 3] = v.w;
+  }
+  float4 q[COUT / 4];
+  const float4* rp = res ? reinterpret_cast<const float4*>(res + m * COUT) : nullptr;
+  if (rp) {
+#pragma unroll
+    for (int o4 = 0; o4 < COUT / 4; ++o4) q[o4] = __ldg(rp + o4);  // issued early: overlaps the FMAs
+  }
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = wts.b[o];
+#pragma unroll
+  for (int k = 0; k < CIN; ++k)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xin[k], wts.w[k * COUT + o], acc[o]);
+  float4* op = reinterpret_cast<float4*>(out + m * COUT);
+#pragma unroll
+  for (int o4 = 0; o4 < COUT / 4; ++o4) {
+    float4 r = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
+    if (rp) {
+      r.x += q[o4].x;
+      r.y += q[o4].y;
+      r.z += q[o4].z;
+      r.w += q[o4].w;
+    }
+    if (relu) {
+      r.x = fmaxf(r.x, 0.f);
+      r.y = fmaxf(r.y, 0.f);
+      r.z = fmaxf(r.z, 0.f);
+      r.w = fmaxf(r.w, 0.f);
+    }
+    op[o4] = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Batched 2-D transpose with leading dimensions: out[b][j][i] = in[b][i][j], i < R, j < Cn.
 // Used for NCHW <-> NHWC at the API boundary (the reference API is NCHW, fear_net.py:58-96).

@@ -292,6 +292,27 @@ def test_fused_stem_block_is_bit_identical(net):
         assert torch.equal(a, b)
 
 
+def test_constant_bank_small_layers_are_bit_identical(net):
+    """Tiny 1x1 layers with their weights passed by value (constant bank) == the shared-memory broadcast kernels."""
+    zt, xt, _, _ = fo.synthetic_crops(3)
+    ref = []
+    for fuse in ("1", "0"):  # with the unfused stem the 16 -> 16 layer of xif1_0 also runs through this kernel
+        net.set_option("fuse_stem", fuse)
+        net.set_option("small_const", "0")
+        try:
+            plain = [net.get_features(zt.cuda()), net.get_features(xt.cuda())]
+            net.set_option("small_const", "1")
+            const = [net.get_features(zt.cuda()), net.get_features(xt.cuda())]
+        finally:
+            net.set_option("small_const", "1")
+            net.set_option("fuse_stem", "1")
+        for a, b in zip(plain, const):
+            assert torch.equal(a, b)
+        ref.append(const)
+    for a, b in zip(*ref):
+        assert torch.equal(a, b)
+
+
 def test_uint8_input_path_is_bit_identical(net):
     """Raw uint8 HWC crops normalised inside the stem kernel == float crops normalised on the host."""
     _, _, zu, xu = fo.synthetic_crops(3)
