@@ -544,6 +544,8 @@ struct PwParams {
   int M, N, NT, num_n_tiles, num_chunks, last_ksteps, relu, stages, stage_bytes, tmem_cols;
   int split_acc;  // 1: hi*hi and the cross terms accumulate separately (long K); 0: one accumulator (K <= 64)
   int acc_stride; // TMEM columns per accumulator stage: 2*NT (main + correction) or NT
+  int w_region;   // > 0: the (hi, lo) weight tile is loaded ONCE into the first w_region bytes of smem (layers with one
+                  // N tile and one K chunk) and the ring stages hold activations only
 };
 
 constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
@@ -554,13 +556,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   const int S = p.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * p.stage_bytes);
+  uint8_t* ring = smem + p.w_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* split = bars + S;
   uint64_t* empty = bars + 2 * S;
   uint64_t* acc_full = bars + 3 * S;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;      // 8 warps x 2 buffers x 2 KB, 512-B aligned
   float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][256] per accumulator stage
 
@@ -589,30 +593,39 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 8);
     }
+    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool resident_w = p.w_region != 0;
 
-  auto a_hi = [&](int s) { return smem + s * p.stage_bytes; };
-  auto a_lo = [&](int s) { return smem + s * p.stage_bytes + kCorrABytes; };
-  auto w_hi = [&](int s) { return smem + s * p.stage_bytes + 2 * kCorrABytes; };
-  auto w_lo = [&](int s) { return smem + s * p.stage_bytes + 2 * kCorrABytes + w_bytes; };
+  auto a_hi = [&](int s) { return ring + s * p.stage_bytes; };
+  auto a_lo = [&](int s) { return ring + s * p.stage_bytes + kCorrABytes; };
+  auto w_hi = [&](int s) { return resident_w ? smem : ring + s * p.stage_bytes + 2 * kCorrABytes; };
+  auto w_lo = [&](int s) { return resident_w ? smem + w_bytes : ring + s * p.stage_bytes + 2 * kCorrABytes + w_bytes; };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (resident_w) {  // one N tile, one K chunk: the weights never change -- fetch them once
+        mbar_arrive_expect_tx(w_full, 2 * w_bytes);
+        tma_load_2d(w_hi(0), &tmWh, w_full, 0, 0);
+        tma_load_2d(w_lo(0), &tmWl, w_full, 0, 0);
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kCorrABytes + 2 * w_bytes);
+          mbar_arrive_expect_tx(&full[stage], resident_w ? kCorrABytes : kCorrABytes + 2 * w_bytes);
           tma_load_2d(a_hi(stage), &tmA, &full[stage], c * 32, mt * 128);
-          tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
-          tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
+          if (!resident_w) {
+            tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
+            tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -626,6 +639,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t idesc2 = umma_idesc_tf32(128, 2 * p.NT);  // stacked [W_hi ; W_lo] (NT <= 128)
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      if (resident_w) mbar_wait(w_full, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -1282,9 +1296,11 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.split_acc = p.num_chunks > 2;
   p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
-  p.stage_bytes = 2 * kCorrABytes + 2 * p.NT * 128;
-  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes) / p.stage_bytes;
-  if (p.stages > 6) p.stages = 6;
+  const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1 && !getenv("FEAR_PW_NO_RESIDENT");
+  p.w_region = resident ? 2 * p.NT * 128 : 0;
+  p.stage_bytes = resident ? 2 * kCorrABytes : 2 * kCorrABytes + 2 * p.NT * 128;
+  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region) / p.stage_bytes;
+  if (p.stages > (resident ? 5 : 6)) p.stages = resident ? 5 : 6;
   if (p.stages < 2) return -22;
   int cols = 32;
   while (cols < 2 * p.acc_stride) cols <<= 1;
@@ -1301,7 +1317,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   CUtensorMap tmC;  // output: [M][N] window of C (pitch ldc); 32 x 16 boxes, SWIZZLE_64B staging; clips the tails
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 + kPwTailBytes;
+  const int smem_bytes = p.w_region + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
   pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, tmC, p);
   return 0;
 }
