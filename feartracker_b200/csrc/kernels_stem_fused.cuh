@@ -84,16 +84,16 @@ stem_xif1_fused_kernel(const __grid_constant__ CUtensorMap tmImg, float* __restr
   }
   tc::mbar_wait(&bar, 0);
   if (U8) {
-    // uint8 HWC bytes -> normalised float planes; pixels outside the image stay exactly 0 (not (0 - mean) / std)
-    for (int pr = warp; pr < kFsPH; pr += kFsThreads / 32) {
-      const int iy = py0 + pr;
-      const bool row_ok = iy >= 0 && iy < H;
-      for (int i = lane; i < (kFsPW + 1) * 3; i += 32) {
-        const int pc = i / 3, ci = i - pc * 3;
-        const int ix = px0 + pc;
-        float v = 0.f;
-        if (row_ok && ix >= 0 && ix < W)
-          v = __fmul_rn(__fsub_rn((float)raw[pr * kFsRawPitch + 4 + i], nrm.mean[ci]), nrm.inv[ci]);
+    // uint8 HWC bytes -> normalised float planes; pixels outside the image stay exactly 0 (not (0 - mean) / std).
+    // One (row, pixel) per thread and iteration: three byte loads, one bounds test, three conflict-free stores.
+    for (int p = threadIdx.x; p < kFsPH * (kFsPW + 1); p += kFsThreads) {
+      const int pr = p / (kFsPW + 1), pc = p - pr * (kFsPW + 1);
+      const int iy = py0 + pr, ix = px0 + pc;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const uint8_t* src = raw + pr * kFsRawPitch + 4 + 3 * pc;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = ok ? __fmul_rn(__fsub_rn((float)src[ci], nrm.mean[ci]), nrm.inv[ci]) : 0.f;
         patch[(ci * kFsPH + pr) * kFsPP + pc] = v;
       }
     }
