@@ -220,8 +220,20 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"  # NCCL's banner / logs go to stderr: stdout is the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry exactly ONE JSON line.  NCCL prints its version banner on stdout when the communicator is
+        # created (NCCL_DEBUG_FILE is read too early to help from here), so fd 1 points at stderr while the process
+        # group and its communicator come up (the barrier forces the lazy creation), then it is restored.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B, total = args.batch, args.batch * world
 
     net = fb.FEARNet(**fb.FEAR_XS_MODEL_KWARGS)

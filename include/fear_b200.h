@@ -121,8 +121,13 @@ int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, floa
 int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream);
 
 /* ---- introspection (tests / bench) ---------------------------------------------------*/
-/* Select a kernel implementation for a stage by name, e.g. ("corr", "ffma" | "tcgen05").
- * Returns FEAR_EINVAL for unknown names.  Default = best validated implementation. */
+/* Select a kernel implementation for a stage by name.  Returns FEAR_EINVAL for unknown names.
+ * Default = best validated implementation; every alternative is parity-tested against it.
+ *   "corr", "pw"   : "auto" | "ffma" | "tcgen05" | "tcgen05ts" | "tcgen05v2"   (correlation / 1x1 convs)
+ *   "dw"           : "auto" | "pixel" | "strip" | "roll" | "tile" | "blocked" | "tma"   (depthwise)
+ *   "fuse_stem"    : "1" (default) stem + xif1_0 in one kernel | "0" four separate kernels
+ *   "small_const"  : "1" (default) tiny 1x1 convs take their weights by value (constant bank) | "0" via smem
+ *   "fuse", "early_sub", "dw_wide" : measured-slower experiments, off by default */
 int fear_set_option(FearContext* h, const char* key, const char* value);
 /* Number of kernels launched by this handle since creation (for bench's gpu_launches). */
 int64_t fear_launch_count(const FearContext* h);
