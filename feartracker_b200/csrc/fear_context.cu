@@ -1159,6 +1159,10 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (!strcmp(key, "pdl")) {  // process-wide: programmatic dependent launch for the TMA / tcgen05 kernels
+    tc::pdl_enabled() = atoi(value) != 0;
+    return 0;
+  }
   if (!strcmp(key, "small_const")) {
     o.small_const = atoi(value) != 0;
     return 0;

@@ -100,6 +100,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_trigger();  // (see tc_common.cuh) the next kernel may start its prologue on SMs we have left ...
+  pdl_wait();     // ... and ours overlapped the previous kernel's tail; its results are visible from here on
 
   // One 4-D box (+ weight slab + biases) per tile, all completing on full[stage].
   auto issue_tile = [&](int tile, int stage) {
@@ -252,7 +254,7 @@ inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, cons
   if (const char* e = getenv("FEAR_EXP_DW")) p.exp_mode = atoi(e);
   int grid = num_sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<grid, GROUPS * kDwGroupWarps * 32, smem, s>>>(tmIn, tmW, tmB, p);
+  if (launch_pdl(kern, dim3(grid), dim3(GROUPS * kDwGroupWarps * 32), (size_t)smem, s, tmIn, tmW, tmB, p) != cudaSuccess) return -31;
   return 0;
 }
 

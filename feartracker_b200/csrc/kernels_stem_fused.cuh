@@ -63,7 +63,6 @@ stem_xif1_fused_kernel(const __grid_constant__ CUtensorMap tmImg, float* __restr
   // patch origin in the image.  The conv needs columns from 2*ox0 - 3; the box starts one column earlier so that the
   // innermost TMA coordinate is 16-byte aligned (floats: column % 4 == 0; uint8: byte 6*ox0 - 16).
   const int py0 = 2 * oy0 - 3, px0 = 2 * ox0 - 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- phase 1: one TMA box brings the input patch in; everything outside the image is zero-filled by the TMA
   //      unit (= the stem conv's padding).  (The first version gathered the patch with ~24 scalar loads per

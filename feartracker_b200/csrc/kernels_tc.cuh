@@ -85,6 +85,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // the next kernel may start its prologue on SMs we have left
+  pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   auto a_hi = [&](int s) { return smem + s * kCorrStageBytes; };
   auto a_lo = [&](int s) { return smem + s * kCorrStageBytes + kCorrABytes; };
@@ -523,7 +525,9 @@ inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int 
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   int exp_mode = 0;
   if (const char* e = getenv("FEAR_EXP_MODE")) exp_mode = atoi(e);
-  corr_tc_kernel<<<grid, kCorrThreads, kCorrSmemBytes, s>>>(tmA, tmB, cat, frames, Bz == 1 ? 0 : B, exp_mode);
+  if (launch_pdl(corr_tc_kernel, dim3(grid), dim3(kCorrThreads), kCorrSmemBytes, s, tmA, tmB, cat, frames, Bz == 1 ? 0 : B,
+                 exp_mode) != cudaSuccess)
+    return -23;
   return 0;
 }
 
@@ -601,6 +605,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool resident_w = p.w_region != 0;
+  pdl_trigger();  // the next kernel may start its prologue on SMs we have left
+  pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   auto a_hi = [&](int s) { return ring + s * p.stage_bytes; };
   auto a_lo = [&](int s) { return ring + s * p.stage_bytes + kCorrABytes; };
@@ -1318,7 +1324,8 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
   const int smem_bytes = p.w_region + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
-  pw_tc_kernel<<<grid, kPwThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, tmC, p);
+  if (launch_pdl(pw_tc_kernel, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, p) != cudaSuccess)
+    return -23;
   return 0;
 }
 

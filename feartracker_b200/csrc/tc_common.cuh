@@ -98,6 +98,29 @@ inline int make_tmap_2d_plain(CUtensorMap* m, const float* base, uint64_t rows, 
   return r == CUDA_SUCCESS ? 0 : -11;
 }
 
+// Launch `kern` with programmatic stream serialization (PDL) unless disabled or the stream is being captured
+// into a CUDA graph (graphs keep the plain launch).
+inline bool& pdl_enabled() {
+  static bool on = false;  // opt-in (fear_set_option "pdl" "1") until validated on the target box
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool use = pdl_enabled() && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+  cfg.attrs = attr;
+  cfg.numAttrs = use ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // Device helpers
 // ------------------------------------------------------------------------------------------
@@ -191,6 +214,14 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch)
+// on SMs the predecessor has already left, then block in pdl_wait() until the predecessor has completed and its
+// writes are visible.  pdl_trigger() lets the *next* kernel do the same with us.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- tcgen05 -----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
