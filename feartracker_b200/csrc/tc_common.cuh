@@ -101,7 +101,7 @@ inline int make_tmap_2d_plain(CUtensorMap* m, const float* base, uint64_t rows, 
 // Launch `kern` with programmatic stream serialization (PDL) unless disabled or the stream is being captured
 // into a CUDA graph (graphs keep the plain launch).
 inline bool& pdl_enabled() {
-  static bool on = false;  // opt-in (fear_set_option "pdl" "1") until validated on the target box
+  static bool on = true;  // fear_set_option("pdl", "0") restores plain stream-ordered launches
   return on;
 }
 template <typename... KArgs, typename... Args>
