@@ -65,6 +65,7 @@ struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
   int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
+  int fuse_dwpw = 0;  // EXPERIMENTAL: 16x16-stage blocks run depthwise + project 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK>)
   int small_const = 1;  // 1: tiny 1x1 layers take their weights by value (constant bank) instead of via shared memory
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
@@ -496,6 +497,20 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
       if (sp.has_pw()) {
         FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
         E = c->bufE;
+      }
+      if (c->opt.fuse_dwpw && tc::available() && sp.stride == 1 && h == 16 && w == 16 && effective(c->opt.pw) == IMPL_TC) {
+        // experimental: depthwise + project 1x1 in one tcgen05 kernel (the depthwise map is never written)
+        float* dst = (i == last - 1 && final_out) ? final_out : Y;
+        LaunchScope scope(c, ST_BACKBONE_PW, s);
+        int r = tc::launch_pw_dw(s, E, B, sp.k, bw.dw.w, bw.dw.b, 1, bw.pwl.w_hi, bw.pwl.w_lo, bw.pwl.b,
+                                 sp.residual() ? X : nullptr, sp.cout, dst, sp.cout, sp.cout, sp.mid(), 0);
+        if (r < 0) return set_err(FEAR_EINVAL, "fused depthwise + 1x1 launch failed (%d)", r);
+        if (r == 0) {
+          FEAR_TRY(check_launch("tc::pw_tc_kernel<DWK>"));
+          if (dst == Y) Y = (X == c->bufS) ? ((Y == c->bufX) ? c->bufY : c->bufX) : X;
+          X = dst;
+          continue;
+        }
       }
       FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
     }
@@ -1161,6 +1176,10 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   Options& o = c ? c->opt : g_default_options;
   if (!strcmp(key, "pdl")) {  // process-wide: programmatic dependent launch for the TMA / tcgen05 kernels
     tc::pdl_enabled() = atoi(value) != 0;
+    return 0;
+  }
+  if (!strcmp(key, "fuse_dwpw")) {
+    o.fuse_dwpw = atoi(value) != 0;
     return 0;
   }
   if (!strcmp(key, "small_const")) {

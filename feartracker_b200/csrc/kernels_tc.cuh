@@ -548,15 +548,26 @@ struct PwParams {
   int M, N, NT, num_n_tiles, num_chunks, last_ksteps, relu, stages, stage_bytes, tmem_cols;
   int split_acc;  // 1: hi*hi and the cross terms accumulate separately (long K); 0: one accumulator (K <= 64)
   int acc_stride; // TMEM columns per accumulator stage: 2*NT (main + correction) or NT
+  // --- fused depthwise producer (pw_tc_kernel<DWK>, DWK = 3 | 5): the A operand is dw(X) computed on the fly ---
+  int dw_relu, dw_bias;  // ReLU / bias of the depthwise stage
+  int box_bytes;         // bytes of one (8 + DWK - 1) x (16 + DWK - 1) x 32-channel input box
   int w_region;   // > 0: the (hi, lo) weight tile is loaded ONCE into the first w_region bytes of smem (layers with one
                   // N tile and one K chunk) and the ring stages hold activations only
 };
 
 constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
 
+// DWK = 0: plain 1x1 conv.  DWK = 3 | 5 (EXPERIMENTAL, opt-in "fuse_dwpw"; 16x16 maps, stride 1): the layer's input is
+// the output of a DWK x DWK depthwise conv that is never materialised -- the producer TMA-loads the depthwise INPUT
+// box of each (128-pixel tile, 32-channel chunk) with its zero-filled halo (tmA is then the 4-D NHWC map of X), two
+// groups of four "split" warps take alternate chunks, run the depthwise conv out of shared memory (same FMA order as
+// dw_tma_kernel => same fp32 values as the unfused pair of kernels) and write the (hi, lo) A tiles directly in the
+// SWIZZLE_128B K-major layout the MMA descriptors expect.  Everything downstream is unchanged.
+template <int DWK>
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
-             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC, const PwParams p) {
+             const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC,
+             const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ CUtensorMap tmDB, const PwParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   const int S = p.stages;
@@ -590,7 +601,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 64) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], 8);
+      mbar_init(&split[s], DWK ? 4 : 8);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -612,6 +623,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto a_lo = [&](int s) { return ring + s * p.stage_bytes + kCorrABytes; };
   auto w_hi = [&](int s) { return resident_w ? smem : ring + s * p.stage_bytes + 2 * kCorrABytes; };
   auto w_lo = [&](int s) { return resident_w ? smem + w_bytes : ring + s * p.stage_bytes + 2 * kCorrABytes + w_bytes; };
+  // fused-depthwise stages: [a_hi][a_lo][w_hi][w_lo][input box][dw weights DWK*DWK x 32][dw bias 32]
+  auto dw_box = [&](int s) { return ring + s * p.stage_bytes + 2 * kCorrABytes + 2 * w_bytes; };
+  auto dw_wts = [&](int s) { return dw_box(s) + p.box_bytes; };
+  auto dw_bia = [&](int s) { return dw_wts(s) + DWK * DWK * 128; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -626,6 +641,20 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if constexpr (DWK > 0) {
+            // 16x16 maps: tile mt = rows [8*(mt&1), +8) of frame mt>>1; the box carries a DWK/2 halo on every side
+            mbar_arrive_expect_tx(&full[stage], p.box_bytes + DWK * DWK * 128 + (p.dw_bias ? 128 : 0) + 2 * w_bytes);
+            tma_load_4d(dw_box(stage), &tmA, &full[stage], c * 32, -(DWK / 2), (mt & 1) * 8 - DWK / 2, mt >> 1);
+            tma_load_2d(dw_wts(stage), &tmDW, &full[stage], c * 32, 0);
+            if (p.dw_bias) tma_load_2d(dw_bia(stage), &tmDB, &full[stage], c * 32, 0);
+            tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
+            tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], resident_w ? kCorrABytes : kCorrABytes + 2 * w_bytes);
           tma_load_2d(a_hi(stage), &tmA, &full[stage], c * 32, mt * 128);
           if (!resident_w) {
@@ -687,6 +716,86 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int ts = threadIdx.x - 64;  // 0..255
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (DWK > 0) {
+      // ---- fused depthwise: group g (4 warps) owns stage g (S == 2); thread = (4-channel group, 2 x 4 pixel block) ----
+      constexpr int K = DWK, IW = 16 + K - 1, TX = 4, TY = 2, NIN = TX + K - 1, NR = TY + K - 1;
+      const int group = (warp - 2) >> 2, gw = (warp - 2) & 3;
+      const int cg = lane & 7, pos = gw * 4 + (lane >> 3);  // 16 positions: 4 across x 4 down
+      const int x0 = (pos & 3) * TX, r0 = (pos >> 2) * TY;
+      int chunk = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int c = 0; c < p.num_chunks; ++c, ++chunk) {
+          if ((chunk & 1) == group) {
+            mbar_wait(&full[stage], phase);
+            const F4* in4 = reinterpret_cast<const F4*>(dw_box(stage));
+            const F4* w4 = reinterpret_cast<const F4*>(dw_wts(stage));
+            F4 acc[TY][TX], bias4;
+            if (p.dw_bias) bias4 = reinterpret_cast<const F4*>(dw_bia(stage))[cg];
+            else bias4.lo = bias4.hi = 0ull;
+#pragma unroll
+            for (int y = 0; y < TY; ++y)
+#pragma unroll
+              for (int i = 0; i < TX; ++i) acc[y][i] = bias4;
+            F4 wk[K][K];
+            const F4* base = in4 + (r0 * IW + x0) * 8 + cg;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              F4 v[NIN];
+#pragma unroll
+              for (int i = 0; i < NIN; ++i) v[i] = base[(r * IW + i) * 8];
+              if (r < K) {
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) wk[r < K ? r : 0][kx] = w4[(r * K + kx) * 8 + cg];
+              }
+#pragma unroll
+              for (int y = 0; y < TY; ++y) {
+                const int ky = r - y;
+                if (ky >= 0 && ky < K) {
+#pragma unroll
+                  for (int kx = 0; kx < K; ++kx) {
+                    const F4 k = wk[(ky >= 0 && ky < K) ? ky : 0][kx];
+#pragma unroll
+                    for (int i = 0; i < TX; ++i) ffma2(acc[y][i].lo, v[i + kx].lo, k.lo);
+#pragma unroll
+                    for (int i = 0; i < TX; ++i) ffma2(acc[y][i].hi, v[i + kx].hi, k.hi);
+                  }
+                }
+              }
+            }
+            uint8_t* ah = a_hi(stage);
+            uint8_t* al = a_lo(stage);
+#pragma unroll
+            for (int y = 0; y < TY; ++y)
+#pragma unroll
+              for (int i = 0; i < TX; ++i) {
+                float4 v = f4_to_float4(acc[y][i]);
+                if (p.dw_relu) {
+                  v.x = fmaxf(v.x, 0.f);
+                  v.y = fmaxf(v.y, 0.f);
+                  v.z = fmaxf(v.z, 0.f);
+                  v.w = fmaxf(v.w, 0.f);
+                }
+                float4 h, l;
+                split_tf32_trunc(v.x, h.x, l.x);
+                split_tf32_trunc(v.y, h.y, l.y);
+                split_tf32_trunc(v.z, h.z, l.z);
+                split_tf32_trunc(v.w, h.w, l.w);
+                const int R = (r0 + y) * 16 + x0 + i;                         // A-tile row = pixel inside the 8 x 16 tile
+                const int off = R * 128 + ((cg ^ (R & 7)) << 4);              // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+                *reinterpret_cast<float4*>(ah + off) = v;                     // raw fp32 = hi operand (hardware truncation)
+                *reinterpret_cast<float4*>(al + off) = l;
+              }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[stage]);
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int c = 0; c < p.num_chunks; ++c) {
         mbar_wait(&full[stage], phase);
@@ -1274,7 +1383,9 @@ inline bool pw_supported(int cin, int cout) {
 
 inline int init_pw() {
   if (cudaFuncSetAttribute(corr_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
     cudaGetLastError();
     return -1;
@@ -1302,6 +1413,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.split_acc = p.num_chunks > 2;
   p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
+  p.dw_relu = p.dw_bias = p.box_bytes = 0;
   const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1 && !getenv("FEAR_PW_NO_RESIDENT");
   p.w_region = resident ? 2 * p.NT * 128 : 0;
   p.stage_bytes = resident ? 2 * kCorrABytes : 2 * kCorrABytes + 2 * p.NT * 128;
@@ -1324,9 +1436,73 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
   const int smem_bytes = p.w_region + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
-  if (launch_pdl(pw_tc_kernel, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, p) != cudaSuccess)
+  if (launch_pdl(pw_tc_kernel<0>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA, tmA, p) !=
+      cudaSuccess)
     return -23;
   return 0;
+}
+
+// EXPERIMENTAL (opt-in "fuse_dwpw", not yet validated on hardware): 1x1 conv whose input is dw_k x dw_k depthwise(X)
+// (+bias, ReLU), X = [B][16][16][K] channels-last, stride 1.  out = act(dw(X) * W^T + bias (+R)).
+// Returns 1 when the shape is not covered (caller runs the two kernels separately).
+inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const float* dw_w, const float* dw_b, int dw_relu,
+                        const float* w_hi, const float* w_lo, const float* bias, const float* R, int ldr, float* C,
+                        int ldc, int N, int K, int relu) {
+  if (!g_tc_ready) return -20;
+  if ((dw_k != 3 && dw_k != 5) || K % 4) return 1;
+  PwParams p;
+  const int M = B * 256;
+  p.bias = bias;
+  p.R = R;
+  p.C = C;
+  p.ldr = ldr;
+  p.ldc = ldc;
+  p.M = M;
+  p.N = N;
+  p.num_chunks = (K + 31) / 32;
+  p.NT = pw_tile_n(N, false);
+  if (!p.NT) return 1;
+  p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
+  p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
+  p.split_acc = p.num_chunks > 2;
+  p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
+  p.relu = relu;
+  p.dw_relu = dw_relu;
+  p.dw_bias = dw_b != nullptr;
+  const int ih = 8 + dw_k - 1, iw = 16 + dw_k - 1;
+  p.box_bytes = ih * iw * 128;
+  p.w_region = 0;
+  p.stage_bytes = (2 * kCorrABytes + 2 * p.NT * 128 + p.box_bytes + dw_k * dw_k * 128 + 128 + 1023) & ~1023;
+  p.stages = 2;  // stage s belongs to split group s
+  if (2 * p.stage_bytes + 1024 + kPwTailBytes > kPwMaxSmem) return 1;
+  int cols = 32;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap tmX, tmWh, tmWl, tmC, tmDW, tmDB;
+  int r = make_tmap_nhwc(&tmX, X, (uint64_t)B, 16, 16, (uint64_t)K, 32, iw, ih);
+  if (r) return r;
+  r = make_tmap_2d(&tmWh, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmWl, w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
+  if (r) return r;
+  r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
+  if (r) return r;
+  r = make_tmap_2d_plain(&tmDW, dw_w, (uint64_t)dw_k * dw_k, (uint64_t)K, dw_k * dw_k, 32);
+  if (r) return r;
+  if (dw_b) {
+    r = make_tmap_2d_plain(&tmDB, dw_b, 1, (uint64_t)K, 1, 32);
+    if (r) return r;
+  } else {
+    tmDB = tmDW;
+  }
+  const int tiles = (M / 128) * p.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const size_t smem_bytes = (size_t)2 * p.stage_bytes + 1024 + kPwTailBytes;
+  cudaError_t e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC,
+                                         tmDW, tmDB, p)
+                            : launch_pdl(pw_tc_kernel<3>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC,
+                                         tmDW, tmDB, p);
+  return e == cudaSuccess ? 0 : -23;
 }
 
 }  // namespace tc

@@ -215,6 +215,26 @@ __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Blackwell packed fp32 FMA (SASS FFMA2): two independent round-to-nearest FMAs on 64-bit register pairs per
+// issue slot.  A scalar 3-register FFMA issues every other cycle per SM sub-partition, so the packed form is what
+// reaches the fp32 peak; the results are bit-identical to two fmaf() calls.
+struct __align__(16) F4 {
+  unsigned long long lo, hi;  // (x, y), (z, w)
+};
+// volatile: keeps the issue order chosen below (runs of FFMA2 sharing one multiplier register, which the operand
+// reuse cache serves -- measured 67 TFLOP/s vs 31-55 TFLOP/s for FFMA2 streams with three fresh operands each).
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float4 f4_to_float4(const F4& v) {
+  float4 r;
+  r.x = __uint_as_float((unsigned)(v.lo & 0xffffffffull));
+  r.y = __uint_as_float((unsigned)(v.lo >> 32));
+  r.z = __uint_as_float((unsigned)(v.hi & 0xffffffffull));
+  r.w = __uint_as_float((unsigned)(v.hi >> 32));
+  return r;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
 // the stream is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch)

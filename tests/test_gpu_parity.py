@@ -313,6 +313,20 @@ def test_constant_bank_small_layers_are_bit_identical(net):
         assert torch.equal(a, b)
 
 
+@pytest.mark.skipif(os.environ.get("FEAR_TEST_EXPERIMENTAL") != "1", reason="opt-in kernels under development")
+def test_experimental_fused_depthwise_project_blocks(net):
+    """EXPERIMENTAL (fuse_dwpw): depthwise + project 1x1 of the 16x16-stage blocks as one tcgen05 kernel.  The
+    depthwise values are computed in the same order as dw_tma_kernel, so the features must not change by a bit."""
+    _, xt, _, _ = fo.synthetic_crops(3)
+    ref = net.get_features(xt.cuda())
+    net.set_option("fuse_dwpw", "1")
+    try:
+        got = net.get_features(xt.cuda())
+    finally:
+        net.set_option("fuse_dwpw", "0")
+    assert torch.equal(ref, got), float((ref - got).abs().max())
+
+
 def test_uint8_input_path_is_bit_identical(net):
     """Raw uint8 HWC crops normalised inside the stem kernel == float crops normalised on the host."""
     _, _, zu, xu = fo.synthetic_crops(3)
