@@ -65,7 +65,8 @@ struct Options {
   int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
   int pw = -1;
   int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
-  int fuse_dwpw = 0;  // EXPERIMENTAL: 16x16-stage blocks run depthwise + project 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK>)
+  int fuse_dwpw = 0;  // EXPERIMENTAL bit mask: 1 = 16x16-stage blocks, 2 = head SepConvs run depthwise + 1x1 as one tcgen05
+                      // kernel (pw_tc_kernel<DWK>)
   int small_const = 1;  // 1: tiny 1x1 layers take their weights by value (constant bank) instead of via shared memory
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
@@ -498,7 +499,7 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
         FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
         E = c->bufE;
       }
-      if (c->opt.fuse_dwpw && tc::available() && sp.stride == 1 && h == 16 && w == 16 && effective(c->opt.pw) == IMPL_TC) {
+      if ((c->opt.fuse_dwpw & 1) && tc::available() && sp.stride == 1 && h == 16 && w == 16 && effective(c->opt.pw) == IMPL_TC) {
         // experimental: depthwise + project 1x1 in one tcgen05 kernel (the depthwise map is never written)
         float* dst = (i == last - 1 && final_out) ? final_out : Y;
         LaunchScope scope(c, ST_BACKBONE_PW, s);
@@ -613,6 +614,21 @@ static int run_features(FearContext* c, cudaStream_t s, const void* img, int B, 
 }
 
 // F: NHWC search features [B][256][256]; zt: [Bz][64][256]; outputs NCHW maps.
+// SepConv of the head (blocks.py:45-72): depthwise 3x3 (no bias, no activation) then 1x1 (+bias, ReLU).
+// With the experimental "fuse_dwpw" bit 2 the pair runs as one tcgen05 kernel (the depthwise map is not written).
+static int launch_sepconv(FearContext* c, cudaStream_t s, const float* X, const DwW& dw, const PwW& pw, float* out,
+                          int ldc, int B) {
+  const int M = B * kScorePix;
+  if ((c->opt.fuse_dwpw & 2) && tc::available() && effective(c->opt.pw) == IMPL_TC) {
+    LaunchScope scope(c, ST_HEAD_PW, s);
+    int r = tc::launch_pw_dw(s, X, B, dw.k, dw.w, dw.b, 0, pw.w_hi, pw.w_lo, pw.b, nullptr, 0, out, ldc, pw.cout, pw.cin, 1);
+    if (r < 0) return set_err(FEAR_EINVAL, "fused SepConv launch failed (%d)", r);
+    if (r == 0) return check_launch("tc::pw_tc_kernel<3>");
+  }
+  FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, X, dw, c->hT, B, kScore, kScore, 1, false));
+  return launch_pw(c, ST_HEAD_PW, s, c->hT, pw.cin, pw, nullptr, 0, out, ldc, M, 1);
+}
+
 static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, const float* F, int B, float* bbox,
                     float* cls) {
   const int M = B * kScorePix;
@@ -621,24 +637,21 @@ static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, con
   for (int br = 0; br < 2; ++br) {
     const BranchW& w = c->branch[br];
     // MatrixMobile: x -> dw3x3 -> 1x1 (+BN) -> ReLU, written into channels [0,256) of the concat buffer
-    FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, F, w.enc_dw, c->hT, B, kScore, kScore, 1, false));
-    FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, w.enc_pw, nullptr, 0, c->hCAT[br], kCatC, M, 1));
+    FEAR_TRY(launch_sepconv(c, s, F, w.enc_dw, w.enc_pw, c->hCAT[br], kCatC, B));
   }
   // pixel-wise correlation of both branches into channels [256,320) of their concat buffers
   FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2, c->zth, c->ztl));
   for (int br = 0; br < 2; ++br) {
     const BranchW& w = c->branch[br];
     // MobileCorrelation.enc: dw3x3(320) -> 1x1 320->256 (+BN) -> ReLU
-    FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, c->hCAT[br], w.corr_dw, c->hT, B, kScore, kScore, 1, false));
-    FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kCatC, w.corr_pw, nullptr, 0, c->hD[br], kFeatC, M, 1));
+    FEAR_TRY(launch_sepconv(c, s, c->hCAT[br], w.corr_dw, w.corr_pw, c->hD[br], kFeatC, B));
   }
   // towers: tower[0] = bbox_tower on reg branch (hD[1]); tower[1] = cls_tower on cls branch (hD[0])
   for (int t = 0; t < 2; ++t) {
     const float* x = c->hD[t == 0 ? 1 : 0];
     float* outs[2] = {c->hP, c->hQ[t]};
     for (int i = 0; i < 2; ++i) {
-      FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, x, c->tower[t].dw[i], c->hT, B, kScore, kScore, 1, false));
-      FEAR_TRY(launch_pw(c, ST_HEAD_PW, s, c->hT, kFeatC, c->tower[t].pw[i], nullptr, 0, outs[i], kFeatC, M, 1));
+      FEAR_TRY(launch_sepconv(c, s, x, c->tower[t].dw[i], c->tower[t].pw[i], outs[i], kFeatC, B));
       x = outs[i];
     }
     FEAR_TRY(launch_dw(c, ST_HEAD_DW, s, x, c->pred_dw[t], c->hT, B, kScore, kScore, 1, false));
@@ -1179,7 +1192,7 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     return 0;
   }
   if (!strcmp(key, "fuse_dwpw")) {
-    o.fuse_dwpw = atoi(value) != 0;
+    o.fuse_dwpw = atoi(value) & 3;  // bit 0: 16x16-stage backbone blocks, bit 1: the head's SepConvs
     return 0;
   }
   if (!strcmp(key, "small_const")) {

@@ -127,6 +127,8 @@ int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* str
  *   "dw"           : "auto" | "pixel" | "strip" | "roll" | "tile" | "blocked" | "tma"   (depthwise)
  *   "fuse_stem"    : "1" (default) stem + xif1_0 in one kernel | "0" four separate kernels
  *   "small_const"  : "1" (default) tiny 1x1 convs take their weights by value (constant bank) | "0" via smem
+ *   "fuse_dwpw"    : EXPERIMENTAL bit mask (default 0): 1 = 16x16-stage blocks, 2 = head SepConvs run their depthwise conv
+ *                    inside the 1x1 GEMM kernel; "pdl": "1" (default) programmatic dependent launch
  *   "fuse", "early_sub", "dw_wide" : measured-slower experiments, off by default */
 int fear_set_option(FearContext* h, const char* key, const char* value);
 /* Number of kernels launched by this handle since creation (for bench's gpu_launches). */

@@ -314,17 +314,23 @@ def test_constant_bank_small_layers_are_bit_identical(net):
 
 
 @pytest.mark.skipif(os.environ.get("FEAR_TEST_EXPERIMENTAL") != "1", reason="opt-in kernels under development")
-def test_experimental_fused_depthwise_project_blocks(net):
-    """EXPERIMENTAL (fuse_dwpw): depthwise + project 1x1 of the 16x16-stage blocks as one tcgen05 kernel.  The
-    depthwise values are computed in the same order as dw_tma_kernel, so the features must not change by a bit."""
-    _, xt, _, _ = fo.synthetic_crops(3)
-    ref = net.get_features(xt.cuda())
-    net.set_option("fuse_dwpw", "1")
+@pytest.mark.parametrize("mask", ["1", "2", "3"])
+def test_experimental_fused_depthwise_pointwise(net, mask):
+    """EXPERIMENTAL (fuse_dwpw): depthwise + 1x1 as one tcgen05 kernel -- bit 0: the 16x16-stage backbone blocks
+    (validated bit-identical on B200 in round 1), bit 1: the head's SepConvs (not yet run on hardware).  The depthwise
+    values are computed in the same order as dw_tma_kernel, so nothing may change by a bit."""
+    zt, xt, _, _ = fo.synthetic_crops(3)
+    zf = net.get_features(zt.cuda())
+    ref_f = net.get_features(xt.cuda())
+    ref = net.track(xt.cuda(), zf)
+    net.set_option("fuse_dwpw", mask)
     try:
-        got = net.get_features(xt.cuda())
+        got_f = net.get_features(xt.cuda())
+        got = net.track(xt.cuda(), zf)
     finally:
         net.set_option("fuse_dwpw", "0")
-    assert torch.equal(ref, got), float((ref - got).abs().max())
+    assert torch.equal(ref_f, got_f), float((ref_f - got_f).abs().max())
+    assert torch.equal(ref[R], got[R]) and torch.equal(ref[C], got[C])
 
 
 def test_uint8_input_path_is_bit_identical(net):
