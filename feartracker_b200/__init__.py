@@ -16,11 +16,28 @@ FEAR_XS_TRACKER_KWARGS = dict(  # reference model_training/config/tracker/siam_t
 
 
 def load_from_lighting(model, checkpoint_path: str, map_location=None, strict: bool = True):
-    """Load a Lightning checkpoint: keep ``model.``-prefixed keys, strip the prefix, strict load
-    (behaviour of reference model_training/utils/torch.py:11-24)."""
+    """Load a Lightning checkpoint the way the reference does (model_training/utils/torch.py:11-24): an int
+    ``map_location`` means ``cuda:<n>``; keys under ``model.`` are kept with the prefix stripped; ``strict=True`` is a
+    strict ``load_state_dict``; ``strict=False`` has pytorch_toolbelt ``transfer_weights`` semantics -- every tensor
+    is loaded on its own and the ones whose name or shape does not match are skipped instead of raising."""
     import torch
 
-    ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=True)
+    if type(map_location) is int:
+        map_location = f"cuda:{map_location}"
+    ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=True)
     sd = {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
-    model.load_state_dict(sd, strict=strict)
+    if strict:
+        model.load_state_dict(sd, strict=True)
+        return model
+    skipped = []
+    for name, value in sd.items():
+        try:
+            model.load_state_dict({name: value}, strict=False)
+        except Exception:  # size mismatch for this tensor: skip it, like transfer_weights
+            skipped.append(name)
+    if skipped:
+        import warnings
+
+        warnings.warn(f"load_from_lighting(strict=False): skipped {len(skipped)} tensors with mismatching shapes "
+                      f"(first: {skipped[0]})")
     return model

@@ -5,7 +5,7 @@ There is no fallback: if the shared object is missing or a call fails, a Runtime
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import numpy as np
 
@@ -39,17 +39,21 @@ _SIGNATURES = {
     "fear_get_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fear_backbone": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fear_head": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "fear_head_update": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "fear_track": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fear_track_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fear_get_features_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fear_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fear_corr_concat_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "fear_corr_concat_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "fear_corr_concat_ws_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fear_corr_nhwc_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "fear_debug_backbone_prefix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fear_debug_head_tensor": (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_void_p]),
     "fear_set_option": (c_int, [c_void_p, c_char_p, c_char_p]),
     "fear_launch_count": (c_int64, [c_void_p]),
+    "fear_generation": (c_int64, [c_void_p]),
     "fear_profile": (c_int, [c_void_p, c_int]),
     "fear_stage_count": (c_int, []),
     "fear_stage_name": (c_char_p, [c_int]),
@@ -57,7 +61,7 @@ _SIGNATURES = {
 }
 
 _lib = None
-_inited_device = None
+_inited_devices = set()
 
 
 def exported_symbols():
@@ -91,12 +95,12 @@ def check(code: int, what: str) -> None:
 
 
 def init(device: int = 0) -> ctypes.CDLL:
-    """Select the device for the library (once per process / device)."""
-    global _inited_device
+    """Initialise the library's per-device state (once per device; several devices per process are fine).
+    ``fear_init`` makes ``device`` current while a handle is packed; the caller's device is restored here."""
     lib = load()
-    if _inited_device != device:
+    if device not in _inited_devices:
         check(lib.fear_init(device), "fear_init")
-        _inited_device = device
+        _inited_devices.add(device)
     return lib
 
 

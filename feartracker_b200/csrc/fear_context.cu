@@ -59,20 +59,17 @@ enum Stage {
 static const char* kStageNames[ST_COUNT] = {"stem",    "backbone_pw", "backbone_dw", "neck",   "head_dw",
                                             "head_pw", "corr",        "pred",        "decode", "layout"};
 
-enum Impl { IMPL_FFMA = 0, IMPL_TC = 1, IMPL_TS = 2, IMPL_TC2 = 3 };  // CUDA cores | tcgen05 A-from-smem | tcgen05 A-from-TMEM
+enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };  // CUDA cores (FFMA baseline / fallback shapes) | tcgen05
 
 struct Options {
-  int corr = -1;  // -1 = auto: tcgen05 (A from smem) when the tensor-core path initialised, else CUDA cores
+  int corr = -1;  // -1 = auto: tcgen05 when the tensor-core path initialised on this device, else CUDA cores
   int pw = -1;
-  int dw_wide = 0;    // 1: 16-wide strips for 5x5 stride-1 depthwise
-  int fuse_dwpw = 0;  // EXPERIMENTAL bit mask: 1 = 16x16-stage blocks, 2 = head SepConvs run depthwise + 1x1 as one tcgen05
-                      // kernel (pw_tc_kernel<DWK>)
-  int small_const = 1;  // 1: tiny 1x1 layers take their weights by value (constant bank) instead of via shared memory
+  int fuse_dwpw = 0;  // bit mask: 1 = 16x16-stage blocks, 2 = head SepConvs run depthwise + 1x1 as one tcgen05 kernel
+                      // (pw_tc_kernel<DWK>); bit-identical to the unfused pair, perf-neutral -> off by default
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
-  int fuse = 0;       // 1 = fused pw-expand + depthwise kernels for the stride-2 blocks (FFMA-bound: measured slower than the tcgen05 GEMM + strip dw pair)
-  int early_sub = 0;  // > 0: run the high-resolution backbone blocks in sub-batches of this many frames
+  int fuse_irf = 1;   // 1: xif2_0 (expand -> depthwise s2 -> project) as ONE tcgen05 kernel (irf_s2_fused_kernel)
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel,
-               // 4 = smem tile, 5 = L1-blocked strip, 6 = TMA pipeline only where it applies (auto also uses it)
+               // 6 = TMA pipeline only where it applies (auto also uses it)
 };
 static Options g_default_options;
 static inline int effective(int impl) { return impl >= 0 ? impl : (tc::available() ? IMPL_TC : IMPL_FFMA); }
@@ -127,14 +124,14 @@ struct FearContext {
   float* ws = nullptr;
   // backbone ping-pong (per frame sizes in floats)
   float *bufX = nullptr, *bufY = nullptr, *bufE = nullptr, *bufD = nullptr;
-  float* bufS = nullptr;  // output of the early (sub-batched) blocks: 32 x 32 x 32 per frame
   // head
   float *hF = nullptr, *hT = nullptr, *hCAT[2] = {nullptr, nullptr}, *hD[2] = {nullptr, nullptr}, *hP = nullptr;
   float* hQ[2] = {nullptr, nullptr};  // tower outputs: [0] = bbox tower (x_reg), [1] = cls tower
   float *zt = nullptr, *mapB = nullptr, *mapC = nullptr;
-  float *zth = nullptr, *ztl = nullptr;  // tf32 (hi, lo) split of zt for the TS correlation
+  float* zu = nullptr;  // dynamic-template (`update`) features of the cls branch, same layout as zt
 
   int64_t launches = 0;
+  int64_t generation = 0;  // bumped whenever workspace pointers or options change (captured CUDA graphs are stale)
   bool profiling = false;
   std::vector<EventPair> events;
   size_t events_used = 0;
@@ -202,35 +199,21 @@ static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, 
     // streaming layers: one pixel per thread on CUDA cores beats a tensor-core tile pipeline here
     LaunchScope scope(c, stage, s);
     const unsigned blocks = (unsigned)((M + 255) / 256);
-    if (c->opt.small_const && w.h_w && w.h_b) {
-      // weights by value in the constant bank (see pw_small_const_kernel)
-      if (w.cin == 16) {
-        PwSmallWeights<16, 16> pw;
-        for (int o = 0; o < 16; ++o)
-          for (int k = 0; k < 16; ++k) pw.w[k * 16 + o] = w.h_w[o * 16 + k];
-        memcpy(pw.b, w.h_b, sizeof(pw.b));
-        pw_small_const_kernel<16, 16><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
-      } else {
-        PwSmallWeights<24, 24> pw;
-        for (int o = 0; o < 24; ++o)
-          for (int k = 0; k < 24; ++k) pw.w[k * 24 + o] = w.h_w[o * 24 + k];
-        memcpy(pw.b, w.h_b, sizeof(pw.b));
-        pw_small_const_kernel<24, 24><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
-      }
-      return check_launch("pw_small_const_kernel");
+    // weights by value in the constant bank (see pw_small_const_kernel)
+    if (w.cin == 16) {
+      PwSmallWeights<16, 16> pw;
+      for (int o = 0; o < 16; ++o)
+        for (int k = 0; k < 16; ++k) pw.w[k * 16 + o] = w.h_w[o * 16 + k];
+      memcpy(pw.b, w.h_b, sizeof(pw.b));
+      pw_small_const_kernel<16, 16><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
+    } else {
+      PwSmallWeights<24, 24> pw;
+      for (int o = 0; o < 24; ++o)
+        for (int k = 0; k < 24; ++k) pw.w[k * 24 + o] = w.h_w[o * 24 + k];
+      memcpy(pw.b, w.h_b, sizeof(pw.b));
+      pw_small_const_kernel<24, 24><<<blocks, 256, 0, s>>>(A, R, C, M, relu, pw);
     }
-    if (w.cin == 16)
-      pw_small_kernel<16, 16><<<blocks, 256, 0, s>>>(A, w.w, w.b, R, C, M, relu);
-    else
-      pw_small_kernel<24, 24><<<blocks, 256, 0, s>>>(A, w.w, w.b, R, C, M, relu);
-    return check_launch("pw_small_kernel");
-  }
-  if (pw_impl == IMPL_TS && tc::pw_supported(w.cin, w.cout) && tc::ts_tile_n(w.cout)) {
-    LaunchScope scope(c, stage, s);
-    int r = tc::launch_gemm_ts(s, A, lda, w.w_hi, w.w_lo, (uint64_t)w.cout, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu,
-                               0, 1, 0);
-    if (r) return set_err(r, "tcgen05 (TS) pw launch failed (%d)", r);
-    return check_launch("tc::gemm_ts");
+    return check_launch("pw_small_const_kernel");
   }
   if (pw_impl == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
     LaunchScope scope(c, stage, s);
@@ -256,7 +239,7 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   const bool want_tma = (c->opt.dw == 6 || c->opt.dw == 3) && tc::available();
   if (want_tma && stride == 2 && w.k == 5 && relu && bias) {
     // 5x5 stride 2: 8x8 output tiles (19x19 input pixels), 4x1 outputs per thread
-    int r = tc::launch_dw_tma_t<5, 2, 8, 8, 4, 1, 4, 2, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, tc::g_num_sms);
+    int r = tc::launch_dw_tma_t<5, 2, 8, 8, 4, 1, 4, 2, true, true>(s, in, w.w, w.b, out, B, H, W, w.c, tc::num_sms());
     if (r < 0) return set_err(FEAR_EINVAL, "TMA depthwise launch failed (%d)", r);
     if (r == 0) return check_launch("tc::dw_tma_kernel<5,2>");
   }
@@ -264,33 +247,13 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   if (want_tma && stride == 1 && w.c >= 24) {
     int r = 1;
 #define DW_TMA(K_, RELU_, BIAS_) \
-  tc::launch_dw_tma_t<K_, 1, 16, 16, 8, 2, 4, 2, RELU_, BIAS_>(s, in, w.w, w.b, out, B, H, W, w.c, tc::g_num_sms)
+  tc::launch_dw_tma_t<K_, 1, 16, 16, 8, 2, 4, 2, RELU_, BIAS_>(s, in, w.w, w.b, out, B, H, W, w.c, tc::num_sms())
     if (w.k == 5 && relu && bias) r = DW_TMA(5, true, true);
     else if (w.k == 3 && relu && bias) r = DW_TMA(3, true, true);
     else if (w.k == 3 && !relu && !bias) r = DW_TMA(3, false, false);
 #undef DW_TMA
     if (r < 0) return set_err(FEAR_EINVAL, "TMA depthwise launch failed (%d)", r);
     if (r == 0) return check_launch("tc::dw_tma_kernel");
-  }
-  // shared-memory tiled kernel: stride 1, maps that are multiples of 16x16, channels in 32-slabs
-  const bool want_tile = c->opt.dw == 4 && stride == 1 && H % 16 == 0 && W % 16 == 0 &&
-                         C4 % 8 == 0 && ((relu && bias) || (!relu && !bias));
-  if (want_tile) {
-    const unsigned blocks = (unsigned)(B * (H / 16) * (W / 16) * (C4 / 8));
-    static bool attr_done = false;
-    if (!attr_done) {
-      CUDA_TRY(cudaFuncSetAttribute(dw_conv_tile_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    dw_tile_smem_bytes<5>()));
-      attr_done = true;
-    }
-    if (w.k == 5 && relu)
-      dw_conv_tile_kernel<5, true, true><<<blocks, 256, dw_tile_smem_bytes<5>(), s>>>(i4, w4, b4, o4, H, W, C4);
-    else if (w.k == 3 && relu)
-      dw_conv_tile_kernel<3, true, true><<<blocks, 256, dw_tile_smem_bytes<3>(), s>>>(i4, w4, b4, o4, H, W, C4);
-    else if (w.k == 3)
-      dw_conv_tile_kernel<3, false, false><<<blocks, 256, dw_tile_smem_bytes<3>(), s>>>(i4, w4, b4, o4, H, W, C4);
-    else return set_err(FEAR_EINVAL, "unsupported tiled depthwise config k=%d", w.k);
-    return check_launch("dw_conv_tile_kernel");
   }
   const bool want_roll = c->opt.dw == 2 || (c->opt.dw == 3 && w.k == 3 && stride == 1);
   if (want_roll && Wo % 4 == 0 && (H / stride) % 16 == 0) {
@@ -314,34 +277,8 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
 #undef ROLL_CASE
     return check_launch("dw_conv_roll_kernel");
   }
-  if (c->opt.dw == 5 && Wo % 4 == 0) {
-    // L1-blocked strip layout: CTA = 32 channels x 4 strips x 8 rows
-    const int TX = stride == 1 ? 4 : 2;
-    const int strips = Wo / TX;
-    const unsigned blocks = (unsigned)((long long)B * (((H / stride) + 7) / 8) * ((strips + 3) / 4) * ((C4 + 7) / 8));
-    if (w.k == 3 && stride == 1 && relu && bias)
-      dw_conv_strip_blocked_kernel<3, 1, 4, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
-    else if (w.k == 3 && stride == 2 && relu && bias)
-      dw_conv_strip_blocked_kernel<3, 2, 2, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
-    else if (w.k == 5 && stride == 1 && relu && bias)
-      dw_conv_strip_blocked_kernel<5, 1, 4, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
-    else if (w.k == 5 && stride == 2 && relu && bias)
-      dw_conv_strip_blocked_kernel<5, 2, 2, true, true><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
-    else if (w.k == 3 && stride == 1 && !relu && !bias)
-      dw_conv_strip_blocked_kernel<3, 1, 4, false, false><<<blocks, 256, 0, s>>>(i4, w4, b4, o4, B, H, W, C4);
-    else
-      return set_err(FEAR_EINVAL, "unsupported depthwise config k=%d s=%d relu=%d bias=%d", w.k, stride, (int)relu,
-                     (int)bias);
-    return check_launch("dw_conv_strip_blocked_kernel");
-  }
   if (c->opt.dw == 3 && w.k == 5 && stride == 1 && Wo % 8 == 0 && relu && bias) {
     // 5x5 stride 1: wide strips (fewer loads per FMA: the kernel is bound by L1 wavefronts, not by HBM)
-    if (Wo % 16 == 0 && c->opt.dw_wide) {
-      const long long total = (long long)B * H * (Wo / 16) * C4;
-      dw_conv_strip_kernel<5, 1, 16, true, true><<<(unsigned)((total + 127) / 128), 128, 0, s>>>(i4, w4, b4, o4, B, H, W,
-                                                                                               C4);
-      return check_launch("dw_conv_strip_kernel<5,1,16>");
-    }
     const long long total = (long long)B * H * (Wo / 8) * C4;
     dw_conv_strip_kernel<5, 1, 8, true, true><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
         i4, w4, b4, o4, B, H, W, C4);
@@ -385,43 +322,6 @@ static int launch_dw(FearContext* c, int stage, cudaStream_t s, const float* in,
   return check_launch("dw_conv_nhwc_kernel");
 }
 
-// Fused pw-expand + depthwise for the stride-2 blocks; returns 1 if this block shape has no fused kernel.
-template <int CIN, int MID, int MSL, int K, int TH, int TW>
-static int launch_fused_one(FearContext* c, cudaStream_t s, const float* X, const BlockW& bw, float* D, int B, int H,
-                            int W) {
-  constexpr int THREADS = 512;
-  constexpr int smem = fused_expand_dw_smem_bytes<CIN, MID, MSL, K, TH, TW>();
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(fused_expand_dw_s2_kernel<CIN, MID, MSL, K, TH, TW, THREADS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
-  const int Ho = H / 2, Wo = W / 2;
-  if (Ho % TH || Wo % TW) return 1;
-  LaunchScope scope(c, ST_BACKBONE_DW, s);
-  const unsigned grid = (unsigned)(B * (Ho / TH) * (Wo / TW));
-  fused_expand_dw_s2_kernel<CIN, MID, MSL, K, TH, TW, THREADS><<<grid, THREADS, smem, s>>>(X, bw.pw.w, bw.pw.b, bw.dw.w,
-                                                                                   bw.dw.b, D, H, W);
-  return check_launch("fused_expand_dw_s2_kernel");
-}
-
-static int launch_fused_expand_dw(FearContext* c, cudaStream_t s, const IrfSpec& sp, const float* X, const BlockW& bw,
-                                  float* D, int B, int H, int W) {
-  if (sp.stride != 2 || !sp.has_pw()) return 1;
-  // (tile, resident channel slice) per block: keep the halo recompute factor low and >= 2 CTAs per SM where possible
-  if (sp.cin == 16 && sp.mid() == 96 && sp.k == 3) return launch_fused_one<16, 96, 96, 3, 8, 4>(c, s, X, bw, D, B, H, W);
-  if (sp.cin == 24 && sp.mid() == 144 && sp.k == 5) {
-    if ((H / 2) % 8 == 0) return launch_fused_one<24, 144, 48, 5, 8, 8>(c, s, X, bw, D, B, H, W);
-    return launch_fused_one<24, 144, 48, 5, 4, 4>(c, s, X, bw, D, B, H, W);
-  }
-  if (sp.cin == 32 && sp.mid() == 192 && sp.k == 5) {
-    if ((H / 2) % 8 == 0) return launch_fused_one<32, 192, 32, 5, 8, 8>(c, s, X, bw, D, B, H, W);
-    return launch_fused_one<32, 192, 32, 5, 4, 4>(c, s, X, bw, D, B, H, W);
-  }
-  return 1;
-}
-
 static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int ldin, long long sIn, float* out,
                             int ldout, long long sOut, int R, int Cn, int batch) {
   LaunchScope scope(c, ST_LAYOUT, s);
@@ -433,36 +333,9 @@ static int launch_transpose(FearContext* c, cudaStream_t s, const float* in, int
 // cat[b, p, 256 + k] = sum_c zt[b, k, c] * cat[b, p, c]    (MobileCorrelation matmul, blocks.py:123)
 // `groups` consecutive [B][256][320] buffers starting at cat share the templates (head: cls + reg branch).
 static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const float* zt, int Bz, float* cat, int B,
-                       int groups, float* zth = nullptr, float* ztl = nullptr) {
+                       int groups) {
   const int corr_impl = effective(opt.corr);
-  if (corr_impl == IMPL_TS && zth && ztl) {
-    {
-      LaunchScope scope(c, ST_LAYOUT, s);  // template features -> tf32 (hi, lo) planes
-      const long long n4 = (long long)Bz * kCorrC * kFeatC / 4;
-      tc::split_hi_lo_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
-          reinterpret_cast<const float4*>(zt), reinterpret_cast<float4*>(zth), reinterpret_cast<float4*>(ztl), n4);
-      FEAR_TRY(check_launch("split_hi_lo_kernel"));
-    }
-    LaunchScope scope(c, ST_CORR, s);
-    int r = tc::launch_gemm_ts(s, cat, kCatC, zth, ztl, (uint64_t)Bz * kCorrC, nullptr, nullptr, 0, cat + kFeatC, kCatC,
-                               B * groups * kScorePix, kCorrC, kFeatC, 0, 2, Bz == 1 ? 1 : B, kCorrC);
-    if (r) return set_err(r, "tcgen05 (TS) corr launch failed (%d)", r);
-    return check_launch("tc::gemm_ts(corr)");
-  }
-  if (corr_impl == IMPL_TC2 && zth && ztl) {
-    {
-      LaunchScope scope(c, ST_LAYOUT, s);  // template features -> tf32 (hi, lo) planes
-      const long long n4 = (long long)Bz * kCorrC * kFeatC / 4;
-      tc::split_hi_lo_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(
-          reinterpret_cast<const float4*>(zt), reinterpret_cast<float4*>(zth), reinterpret_cast<float4*>(ztl), n4);
-      FEAR_TRY(check_launch("split_hi_lo_kernel"));
-    }
-    LaunchScope scope(c, ST_CORR, s);
-    int r = tc::launch_corr2(s, zth, ztl, Bz, cat, B, groups);
-    if (r) return set_err(r, "tcgen05 (v2) corr launch failed (%d)", r);
-    return check_launch("tc::corr2");
-  }
-  if (corr_impl == IMPL_TC || corr_impl == IMPL_TS || corr_impl == IMPL_TC2) {
+  if (corr_impl == IMPL_TC) {
     LaunchScope scope(c, ST_CORR, s);
     int r = tc::launch_corr(s, zt, Bz, cat, B, groups);
     if (r) return set_err(r, "tcgen05 corr launch failed (%d)", r);
@@ -478,50 +351,44 @@ static int launch_corr(FearContext* c, const Options& opt, cudaStream_t s, const
 }
 
 // ------------------------------------------------------------------------------ executor
-// img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer)
-// Run backbone blocks [first, last) on NHWC activations X (B frames of h x w).  The last block's output goes to
-// `final_out` when given (else into a ping-pong buffer); *out receives the output pointer, h/w are updated.
+// Run backbone blocks [first, last) on NHWC activations X (B frames of h x w), ping-ponging between bufX and bufY
+// (bufE = expanded tensor, bufD = depthwise output of the block in flight).  *out receives the output pointer,
+// h / w are updated.
 static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, int& w, int first, int last,
-                      float* final_out, float** out) {
+                      float** out) {
   float* Y = (X == c->bufX) ? c->bufY : c->bufX;
   for (int i = first; i < last; ++i) {
     const IrfSpec& sp = kBlocks[i];
     const BlockW& bw = c->blocks[i];
     const int M = B * h * w;
-    int fused = 1;
-    if (c->opt.fuse) {
-      fused = launch_fused_expand_dw(c, s, sp, X, bw, c->bufD, B, h, w);
-      if (fused < 0 || fused > 1) return fused;
+    const float* E = X;
+    if (sp.has_pw()) {
+      FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
+      E = c->bufE;
     }
-    if (fused == 1) {  // unfused: materialise the expanded tensor, then the depthwise conv
-      const float* E = X;
-      if (sp.has_pw()) {
-        FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
-        E = c->bufE;
+    if ((c->opt.fuse_dwpw & 1) && tc::available() && sp.stride == 1 && h == 16 && w == 16 &&
+        effective(c->opt.pw) == IMPL_TC) {
+      // depthwise + project 1x1 in one tcgen05 kernel (the depthwise map is never written)
+      LaunchScope scope(c, ST_BACKBONE_PW, s);
+      int r = tc::launch_pw_dw(s, E, B, sp.k, bw.dw.w, bw.dw.b, 1, bw.pwl.w_hi, bw.pwl.w_lo, bw.pwl.b,
+                               sp.residual() ? X : nullptr, sp.cout, Y, sp.cout, sp.cout, sp.mid(), 0);
+      if (r < 0) return set_err(FEAR_EINVAL, "fused depthwise + 1x1 launch failed (%d)", r);
+      if (r == 0) {
+        FEAR_TRY(check_launch("tc::pw_tc_kernel<DWK>"));
+        float* t = X;
+        X = Y;
+        Y = t;
+        continue;
       }
-      if ((c->opt.fuse_dwpw & 1) && tc::available() && sp.stride == 1 && h == 16 && w == 16 && effective(c->opt.pw) == IMPL_TC) {
-        // experimental: depthwise + project 1x1 in one tcgen05 kernel (the depthwise map is never written)
-        float* dst = (i == last - 1 && final_out) ? final_out : Y;
-        LaunchScope scope(c, ST_BACKBONE_PW, s);
-        int r = tc::launch_pw_dw(s, E, B, sp.k, bw.dw.w, bw.dw.b, 1, bw.pwl.w_hi, bw.pwl.w_lo, bw.pwl.b,
-                                 sp.residual() ? X : nullptr, sp.cout, dst, sp.cout, sp.cout, sp.mid(), 0);
-        if (r < 0) return set_err(FEAR_EINVAL, "fused depthwise + 1x1 launch failed (%d)", r);
-        if (r == 0) {
-          FEAR_TRY(check_launch("tc::pw_tc_kernel<DWK>"));
-          if (dst == Y) Y = (X == c->bufS) ? ((Y == c->bufX) ? c->bufY : c->bufX) : X;
-          X = dst;
-          continue;
-        }
-      }
-      FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
     }
+    FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
     h /= sp.stride;
     w /= sp.stride;
-    float* dst = (i == last - 1 && final_out) ? final_out : Y;
-    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, dst,
+    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, Y,
                        sp.cout, B * h * w, 0));
-    if (dst == Y) Y = (X == c->bufS) ? ((Y == c->bufX) ? c->bufY : c->bufX) : X;
-    X = dst;
+    float* t = X;
+    X = Y;
+    Y = t;
   }
   *out = X;
   return 0;
@@ -539,68 +406,48 @@ static StemNorm imagenet_norm() {
   return n;
 }
 
-constexpr int kEarlyBlocks = 5;  // xif1_0 .. xif3_0: the high-resolution part (128^2 / 64^2 maps at 256^2 input)
-
-// img (B,3,H,W) NCHW -> NHWC backbone features [B][H/16 * W/16][112] left in *feat (a workspace buffer).
-// With opt.early_sub > 0 the high-resolution blocks run in sub-batches of that many frames so that their
-// (6x expanded) intermediates stay resident in the 126 MB L2 instead of round-tripping through HBM.
+// img (B,3,H,W) NCHW fp32 -- or raw uint8 (B,H,W,3) with u8 = true -- -> NHWC backbone features
+// [B][H/16 * W/16][112] left in *feat (a workspace buffer).
 static int run_backbone(FearContext* c, cudaStream_t s, const void* img, int B, int H, int W, const float** feat,
                         bool u8 = false) {
-  const int sub = (c->opt.early_sub > 0 && c->opt.early_sub < B) ? c->opt.early_sub : B;
-  const bool blocked = sub < B;
-  const int eh = H / 8, ew = W / 8;                      // map size after the early blocks (stride 8)
-  const long long per_frame_s = (long long)eh * ew * kBlocks[kEarlyBlocks - 1].cout;
-  float* X = nullptr;
-  int h = H / 2, w = W / 2;
-  for (int b0 = 0; b0 < B; b0 += sub) {
-    const int nb = (B - b0 < sub) ? B - b0 : sub;
-    // (TMA needs 16-byte aligned image rows and base: W % 16 == 0 covers both layouts)
-    const bool fuse_stem = c->opt.fuse_stem && tc::available() && (H / 2) % kFsTH == 0 && (W / 2) % kFsTW == 0 &&
-                           (reinterpret_cast<uintptr_t>(img) & 15) == 0;
-    if (fuse_stem) {
-      // stem + xif1_0 (dw3x3 -> 1x1 + residual) in one pass over the image: the block output lands in bufX
-      LaunchScope scope(c, ST_STEM, s);
-      static bool attr_done = false;
-      if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
-        CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
-        attr_done = true;
-      }
-      const unsigned blocks = (unsigned)((long long)nb * ((H / 2) / kFsTH) * ((W / 2) / kFsTW));
-      CUtensorMap tm;
-      if (u8) {
-        const uint8_t* base = static_cast<const uint8_t*>(img) + (long long)b0 * 3 * H * W;
-        int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, base, (uint64_t)3 * W, (uint64_t)H, (uint64_t)nb,
-                                 (uint64_t)3 * W, (uint64_t)3 * W * H, kFsRawPitch, kFsPH, 1);
-        if (r) return set_err(FEAR_EINVAL, "tensor map for the uint8 image failed (%d)", r);
-        stem_xif1_fused_kernel<true><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, imagenet_norm(), c->fs);
-      } else {
-        const float* base = static_cast<const float*>(img) + (long long)b0 * 3 * H * W;
-        int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, (uint64_t)W, (uint64_t)H, (uint64_t)3 * nb,
-                                 (uint64_t)W * 4, (uint64_t)W * H * 4, kFsPP, kFsPH, 3);
-        if (r) return set_err(FEAR_EINVAL, "tensor map for the float image failed (%d)", r);
-        stem_xif1_fused_kernel<false><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, StemNorm(), c->fs);
-      }
-      FEAR_TRY(check_launch("stem_xif1_fused_kernel"));
-    } else {
-      LaunchScope scope(c, ST_STEM, s);
-      const unsigned blocks = (unsigned)((long long)nb * ((H / 2 + 3) / 4) * ((W / 2 + 31) / 32));
-      if (u8)
-        stem_conv3x3s2_kernel<true><<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(img) + (long long)b0 * 3 * H * W,
-                                                           c->stem_w, c->stem_b, c->bufX, nb, H, W, imagenet_norm());
-      else
-        stem_conv3x3s2_kernel<false><<<blocks, 128, 0, s>>>(static_cast<const float*>(img) + (long long)b0 * 3 * H * W,
-                                                            c->stem_w, c->stem_b, c->bufX, nb, H, W, StemNorm());
-      FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
+  // (TMA needs 16-byte aligned image rows and base: W % 16 == 0 covers both layouts)
+  const bool fuse_stem = c->opt.fuse_stem && tc::available() && (H / 2) % kFsTH == 0 && (W / 2) % kFsTW == 0 &&
+                         (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+  if (fuse_stem) {
+    // stem + xif1_0 (dw3x3 -> 1x1 + residual) in one pass over the image: the block output lands in bufX
+    LaunchScope scope(c, ST_STEM, s);
+    if (tc::attr_needed(reinterpret_cast<const void*>(stem_xif1_fused_kernel<true>))) {
+      CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
+      CUDA_TRY(cudaFuncSetAttribute(stem_xif1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFsSmemBytes));
     }
-    h = H / 2;
-    w = W / 2;
-    FEAR_TRY(run_blocks(c, s, c->bufX, nb, h, w, fuse_stem ? 1 : 0, kEarlyBlocks,
-                        blocked ? c->bufS + b0 * per_frame_s : nullptr, &X));
+    const unsigned blocks = (unsigned)((long long)B * ((H / 2) / kFsTH) * ((W / 2) / kFsTW));
+    CUtensorMap tm;
+    if (u8) {
+      int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, img, (uint64_t)3 * W, (uint64_t)H, (uint64_t)B,
+                               (uint64_t)3 * W, (uint64_t)3 * W * H, kFsRawPitch, kFsPH, 1);
+      if (r) return set_err(FEAR_EINVAL, "tensor map for the uint8 image failed (%d)", r);
+      stem_xif1_fused_kernel<true><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, imagenet_norm(), c->fs);
+    } else {
+      int r = tc::make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, img, (uint64_t)W, (uint64_t)H, (uint64_t)3 * B,
+                               (uint64_t)W * 4, (uint64_t)W * H * 4, kFsPP, kFsPH, 3);
+      if (r) return set_err(FEAR_EINVAL, "tensor map for the float image failed (%d)", r);
+      stem_xif1_fused_kernel<false><<<blocks, kFsThreads, kFsSmemBytes, s>>>(tm, c->bufX, H, W, StemNorm(), c->fs);
+    }
+    FEAR_TRY(check_launch("stem_xif1_fused_kernel"));
+  } else {
+    LaunchScope scope(c, ST_STEM, s);
+    const unsigned blocks = (unsigned)((long long)B * ((H / 2 + 3) / 4) * ((W / 2 + 31) / 32));
+    if (u8)
+      stem_conv3x3s2_kernel<true><<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(img), c->stem_w, c->stem_b, c->bufX,
+                                                         B, H, W, imagenet_norm());
+    else
+      stem_conv3x3s2_kernel<false><<<blocks, 128, 0, s>>>(static_cast<const float*>(img), c->stem_w, c->stem_b, c->bufX,
+                                                          B, H, W, StemNorm());
+    FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
   }
-  if (blocked) X = c->bufS;
+  int h = H / 2, w = W / 2;
   float* out = nullptr;
-  FEAR_TRY(run_blocks(c, s, X, B, h, w, kEarlyBlocks, kNumBlocks, nullptr, &out));
+  FEAR_TRY(run_blocks(c, s, c->bufX, B, h, w, fuse_stem ? 1 : 0, kNumBlocks, &out));
   *feat = out;
   return 0;
 }
@@ -629,8 +476,10 @@ static int launch_sepconv(FearContext* c, cudaStream_t s, const float* X, const 
   return launch_pw(c, ST_HEAD_PW, s, c->hT, pw.cin, pw, nullptr, 0, out, ldc, M, 1);
 }
 
+// zu (optional): dynamic-template features [Bu][64][256] for the classification branch (BoxTower.forward's `update`
+// argument, blocks.py:174-179: cls_encode(update, search) -- the regression branch keeps the original template).
 static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, const float* F, int B, float* bbox,
-                    float* cls) {
+                    float* cls, const float* zu = nullptr, int Bu = 0) {
   const int M = B * kScorePix;
   // the two concat buffers are laid out back to back for THIS batch so one correlation launch covers both
   c->hCAT[1] = c->hCAT[0] + (long long)B * kScorePix * kCatC;
@@ -640,7 +489,12 @@ static int run_head(FearContext* c, cudaStream_t s, const float* zt, int Bz, con
     FEAR_TRY(launch_sepconv(c, s, F, w.enc_dw, w.enc_pw, c->hCAT[br], kCatC, B));
   }
   // pixel-wise correlation of both branches into channels [256,320) of their concat buffers
-  FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2, c->zth, c->ztl));
+  if (zu) {
+    FEAR_TRY(launch_corr(c, c->opt, s, zu, Bu, c->hCAT[0], B, 1));  // cls branch <- update template
+    FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[1], B, 1));  // reg branch <- kernel template
+  } else {
+    FEAR_TRY(launch_corr(c, c->opt, s, zt, Bz, c->hCAT[0], B, 2));
+  }
   for (int br = 0; br < 2; ++br) {
     const BranchW& w = c->branch[br];
     // MobileCorrelation.enc: dw3x3(320) -> 1x1 320->256 (+BN) -> ReLU
@@ -674,12 +528,24 @@ static int run_decode(FearContext* c, cudaStream_t s, const float* bbox, const f
 }
 
 // ------------------------------------------------------------------------------ C ABI
-static bool g_inited = false;
-static int g_device = 0;
+// RAII: make the handle's device current for the duration of a C entry point, restore the caller's on exit.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
 
 extern "C" int fear_abi_version(void) { return FEAR_ABI_VERSION; }
 extern "C" const char* fear_last_error(void) { return g_err; }
 
+// Per-device initialisation; may be called for several devices of one process (each handle remembers its own).
+// Leaves `device` current (the reference's `.cuda(cuda_id)` convention); later entry points never change the
+// caller's current device.
 extern "C" int fear_init(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -690,8 +556,7 @@ extern "C" int fear_init(int device) {
   if (p.major != 10)
     return set_err(FEAR_ENODEV, "device %d is sm_%d%d; libfear_b200 is built for sm_100a only", device, p.major, p.minor);
   CUDA_TRY(cudaSetDevice(device));
-  g_device = device;
-  g_inited = true;
+  if (tc::dev_state().inited) return 0;
   return tc::init();
 }
 
@@ -708,7 +573,9 @@ extern "C" int fear_stage_count(void) { return ST_COUNT; }
 extern "C" const char* fear_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : nullptr; }
 
 extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int n, FearContext** handle) {
-  if (!g_inited) return set_err(FEAR_ESTATE, "fear_init() has not been called");
+  int cur_dev = 0;
+  CUDA_TRY(cudaGetDevice(&cur_dev));
+  if (!tc::dev_state().inited) return set_err(FEAR_ESTATE, "fear_init() has not been called for device %d", cur_dev);
   if (!blob || !offsets || !handle) return set_err(FEAR_EINVAL, "null argument");
   const auto& table = weight_table();
   if (n != (int)table.size()) return set_err(FEAR_EINVAL, "expected %d tensors, got %d", (int)table.size(), n);
@@ -767,7 +634,7 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
   arena.resize((arena.size() + 63) & ~(size_t)63, 0.f);
 
   FearContext* c = new FearContext();
-  c->device = g_device;
+  c->device = cur_dev;
   c->opt = g_default_options;
   cudaError_t e = cudaMalloc(&c->d_weights, arena.size() * sizeof(float));
   if (e != cudaSuccess) {
@@ -870,6 +737,7 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
   if (!c) return set_err(FEAR_ESTATE, "null handle");
   if (max_batch < 1) return set_err(FEAR_EINVAL, "max_batch must be >= 1");
   if (max_batch <= c->reserved) return 0;
+  DeviceGuard guard(c->device);
   CUDA_TRY(cudaDeviceSynchronize());
   if (c->ws) cudaFree(c->ws);
   c->ws = nullptr;
@@ -884,8 +752,7 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
       (int64_t)kScorePix * kFeatC, (int64_t)kScorePix * kFeatC,     // hQ[2]
       (int64_t)kTmplPix * kFeatC,                                   // zt
       4 * kScorePix, kScorePix,                                     // mapB mapC
-      (int64_t)kTmplPix * kFeatC, (int64_t)kTmplPix * kFeatC,       // zth ztl
-      32 * 32 * 32,                                                 // bufS
+      (int64_t)kTmplPix * kFeatC,                                   // zu
   };
   int64_t total = 0;
   std::vector<int64_t> offs;
@@ -914,15 +781,15 @@ extern "C" int fear_reserve(FearContext* c, int max_batch) {
   c->zt = p + offs[13];
   c->mapB = p + offs[14];
   c->mapC = p + offs[15];
-  c->zth = p + offs[16];
-  c->ztl = p + offs[17];
-  c->bufS = p + offs[18];
+  c->zu = p + offs[16];
+  c->generation++;
   c->reserved = max_batch;
   return 0;
 }
 
 extern "C" void fear_free(FearContext* c) {
   if (!c) return;
+  DeviceGuard guard(c->device);
   cudaDeviceSynchronize();
   for (auto& ev : c->events) {
     cudaEventDestroy(ev.a);
@@ -940,6 +807,7 @@ static int check_ctx(FearContext* c) {
 
 extern "C" int fear_get_features(FearContext* c, const float* d_img, int B, int H, int W, float* d_feat, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_img || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
     return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
@@ -956,6 +824,7 @@ extern "C" int fear_get_features(FearContext* c, const float* d_img, int B, int 
 
 extern "C" int fear_backbone(FearContext* c, const float* d_img, int B, int H, int W, float* d_feat, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_img || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
     return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
@@ -977,23 +846,40 @@ static int stage_template(FearContext* c, cudaStream_t s, const float* d_zfeat, 
                           (long long)kTmplPix * kFeatC, kFeatC, kTmplPix, nz);
 }
 
-extern "C" int fear_head(FearContext* c, const float* d_zfeat, int Bz, const float* d_xfeat, int B, float* d_bbox,
-                         float* d_cls, void* stream) {
+// zfeat NCHW (n,256,8,8) -> dst chunk [n][64][256]
+static int stage_template_to(FearContext* c, cudaStream_t s, const float* d_zfeat, int nz, float* dst) {
+  return launch_transpose(c, s, d_zfeat, kTmplPix, (long long)kFeatC * kTmplPix, dst, kFeatC,
+                          (long long)kTmplPix * kFeatC, kFeatC, kTmplPix, nz);
+}
+
+extern "C" int fear_head_update(FearContext* c, const float* d_zfeat, int Bz, const float* d_zupdate, int Bu,
+                                const float* d_xfeat, int B, float* d_bbox, float* d_cls, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_zfeat || !d_xfeat || !d_bbox || !d_cls || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  if (d_zupdate && Bu != 1 && Bu != B)
+    return set_err(FEAR_EINVAL, "update-template batch must be 1 or B (got %d vs %d)", Bu, B);
   cudaStream_t s = (cudaStream_t)stream;
   if (Bz == 1) FEAR_TRY(stage_template(c, s, d_zfeat, 1));
+  if (d_zupdate && Bu == 1) FEAR_TRY(stage_template_to(c, s, d_zupdate, 1, c->zu));
   for (int b0 = 0; b0 < B; b0 += c->reserved) {
     const int nb = (B - b0 < c->reserved) ? B - b0 : c->reserved;
     if (Bz != 1) FEAR_TRY(stage_template(c, s, d_zfeat + (long long)b0 * kFeatC * kTmplPix, nb));
+    if (d_zupdate && Bu != 1)
+      FEAR_TRY(stage_template_to(c, s, d_zupdate + (long long)b0 * kFeatC * kTmplPix, nb, c->zu));
     FEAR_TRY(launch_transpose(c, s, d_xfeat + (long long)b0 * kFeatC * kScorePix, kScorePix,
                               (long long)kFeatC * kScorePix, c->hF, kFeatC, (long long)kScorePix * kFeatC, kFeatC,
                               kScorePix, nb));
     FEAR_TRY(run_head(c, s, c->zt, Bz == 1 ? 1 : nb, c->hF, nb, d_bbox + (long long)b0 * 4 * kScorePix,
-                      d_cls + (long long)b0 * kScorePix));
+                      d_cls + (long long)b0 * kScorePix, d_zupdate ? c->zu : nullptr, Bu == 1 ? 1 : nb));
   }
   return 0;
+}
+
+extern "C" int fear_head(FearContext* c, const float* d_zfeat, int Bz, const float* d_xfeat, int B, float* d_bbox,
+                         float* d_cls, void* stream) {
+  return fear_head_update(c, d_zfeat, Bz, nullptr, 0, d_xfeat, B, d_bbox, d_cls, stream);
 }
 
 static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, const void* d_search,
@@ -1025,6 +911,7 @@ static int track_impl(FearContext* c, cudaStream_t s, const float* d_template, c
 extern "C" int fear_track(FearContext* c, const float* d_search, const float* d_zfeat, int Bz, int B, float* d_bbox,
                           float* d_cls, FearBox* d_boxes, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_search || !d_zfeat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
@@ -1034,6 +921,7 @@ extern "C" int fear_track(FearContext* c, const float* d_search, const float* d_
 extern "C" int fear_track_u8(FearContext* c, const uint8_t* d_search_u8, const float* d_zfeat, int Bz, int B,
                              float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_search_u8 || !d_zfeat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
   if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
@@ -1043,6 +931,7 @@ extern "C" int fear_track_u8(FearContext* c, const uint8_t* d_search_u8, const f
 extern "C" int fear_get_features_u8(FearContext* c, const uint8_t* d_img_u8, int B, int H, int W, float* d_feat,
                                     void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_img_u8 || !d_feat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (H % 16 || W % 16 || H < 16 || W < 16 || H > 256 || W > 256)
     return set_err(FEAR_EINVAL, "H, W must be multiples of 16 in [16, 256] (got %dx%d)", H, W);
@@ -1060,6 +949,7 @@ extern "C" int fear_get_features_u8(FearContext* c, const uint8_t* d_img_u8, int
 extern "C" int fear_forward(FearContext* c, const float* d_template, const float* d_search, int B, float* d_bbox,
                             float* d_cls, FearBox* d_boxes, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_template || !d_search || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (!d_boxes && (!d_bbox || !d_cls)) return set_err(FEAR_EINVAL, "no output requested");
   return track_impl(c, (cudaStream_t)stream, d_template, d_search, nullptr, B, B, d_bbox, d_cls, d_boxes);
@@ -1071,68 +961,59 @@ extern "C" int fear_decode(const float* d_bbox, const float* d_cls, int B, int a
   return run_decode(nullptr, (cudaStream_t)stream, d_bbox, d_cls, B, apply_sigmoid, d_boxes);
 }
 
-// second scratch (hi/lo template planes of the handle-less channels-last correlation)
-static float* g_scratch2 = nullptr;
-static size_t g_scratch2_floats = 0;
-static int ensure_scratch2(size_t need) {
-  if (need <= g_scratch2_floats) return 0;
-  CUDA_TRY(cudaDeviceSynchronize());
-  if (g_scratch2) cudaFree(g_scratch2);
-  g_scratch2 = nullptr;
-  g_scratch2_floats = 0;
-  CUDA_TRY(cudaMalloc(&g_scratch2, need * sizeof(float)));
-  g_scratch2_floats = need;
-  return 0;
-}
-
 extern "C" int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* stream) {
   if (!d_zt || !d_cat || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
-  float *zth = nullptr, *ztl = nullptr;
-  if (effective(g_default_options.corr) == IMPL_TS || effective(g_default_options.corr) == IMPL_TC2) {
-    const size_t need = 2 * (size_t)Bz * kCorrC * kFeatC;
-    FEAR_TRY(ensure_scratch2(need));
-    zth = g_scratch2;
-    ztl = g_scratch2 + (size_t)Bz * kCorrC * kFeatC;
-  }
-  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B, 1, zth, ztl);
+  if (!tc::dev_state().inited) return set_err(FEAR_ESTATE, "fear_init() has not been called for the current device");
+  return launch_corr(nullptr, g_default_options, (cudaStream_t)stream, d_zt, Bz, d_cat, B, 1);
 }
 
-// Scratch for the handle-less NCHW wrapper; grows (cudaMalloc) only when a larger batch arrives.
-static float* g_scratch = nullptr;
-static size_t g_scratch_floats = 0;
+extern "C" size_t fear_corr_concat_workspace_bytes(int B, int Bz) {
+  if (B < 1 || Bz < 1) return 0;
+  return ((size_t)B * kScorePix * kCatC + (size_t)Bz * kCorrC * kFeatC) * sizeof(float);
+}
 
-extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* stream) {
-  if (!d_z || !d_x || !d_out || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+// NCHW in / NCHW out through the hot path's channels-last tcgen05 kernel; the two layout changes use the
+// caller's workspace (nothing is allocated, the stream is never synchronised).
+extern "C" int fear_corr_concat_ws_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* d_workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (!d_z || !d_x || !d_out || !d_workspace || B < 1) return set_err(FEAR_EINVAL, "bad argument");
   if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  if (workspace_bytes < fear_corr_concat_workspace_bytes(B, Bz) || (reinterpret_cast<uintptr_t>(d_workspace) & 1023))
+    return set_err(FEAR_EINVAL, "workspace must be 1024-byte aligned and hold fear_corr_concat_workspace_bytes(B, Bz) = %zu bytes",
+                   fear_corr_concat_workspace_bytes(B, Bz));
+  if (!tc::dev_state().inited) return set_err(FEAR_ESTATE, "fear_init() has not been called for the current device");
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t need = (size_t)B * kScorePix * kCatC + 3 * (size_t)Bz * kCorrC * kFeatC;
-  if (need > g_scratch_floats) {
-    CUDA_TRY(cudaDeviceSynchronize());
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    g_scratch_floats = 0;
-    CUDA_TRY(cudaMalloc(&g_scratch, need * sizeof(float)));
-    g_scratch_floats = need;
-  }
-  float* cat = g_scratch;
-  float* zt = g_scratch + (size_t)B * kScorePix * kCatC;
+  float* cat = static_cast<float*>(d_workspace);
+  float* zt = cat + (size_t)B * kScorePix * kCatC;
   // z [c][k] -> zt [k][c];  x [c][p] -> cat[p][0:256]
   FEAR_TRY(launch_transpose(nullptr, s, d_z, kCorrC, (long long)kFeatC * kCorrC, zt, kFeatC, (long long)kCorrC * kFeatC,
                             kFeatC, kCorrC, Bz));
   FEAR_TRY(launch_transpose(nullptr, s, d_x, kScorePix, (long long)kFeatC * kScorePix, cat, kCatC,
                             (long long)kScorePix * kCatC, kFeatC, kScorePix, B));
-  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B, 1, zt + (size_t)Bz * kCorrC * kFeatC,
-                       zt + 2 * (size_t)Bz * kCorrC * kFeatC));
+  FEAR_TRY(launch_corr(nullptr, g_default_options, s, zt, Bz, cat, B, 1));
   // cat [p][320] -> out [320][p]
   return launch_transpose(nullptr, s, cat, kCatC, (long long)kScorePix * kCatC, d_out, kScorePix,
                           (long long)kCatC * kScorePix, kScorePix, kCatC, B);
+}
+
+// Workspace-free form with the signature SURVEY.md 8(b) lists: a direct CUDA-core kernel on the reference's own
+// layouts (compatibility entry point -- the hot path and the _ws form above use the tcgen05 kernel).
+extern "C" int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* stream) {
+  if (!d_z || !d_x || !d_out || B < 1) return set_err(FEAR_EINVAL, "bad argument");
+  if (Bz != 1 && Bz != B) return set_err(FEAR_EINVAL, "template batch must be 1 or B (got %d vs %d)", Bz, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpy2DAsync(d_out, (size_t)kCatC * kScorePix * sizeof(float), d_x, (size_t)kFeatC * kScorePix * sizeof(float),
+                             (size_t)kFeatC * kScorePix * sizeof(float), (size_t)B, cudaMemcpyDeviceToDevice, s));
+  corr_nchw_ffma_kernel<<<dim3(kScorePix / 64, B), 256, 0, s>>>(d_z, Bz == 1 ? 0ll : (long long)kFeatC * kCorrC, d_x, d_out);
+  return check_launch("corr_nchw_ffma_kernel");
 }
 
 // ---- debug / introspection of intermediates (tests localise a mismatch with these) ----------
 extern "C" int fear_debug_backbone_prefix(FearContext* c, const float* d_img, int B, int H, int W, int nblocks,
                                           float* d_out, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!d_img || !d_out || B < 1 || B > c->reserved || nblocks < 0 || nblocks > kNumBlocks)
     return set_err(FEAR_EINVAL, "bad argument (B must be <= reserved batch)");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1169,6 +1050,7 @@ extern "C" int fear_debug_backbone_prefix(FearContext* c, const float* d_img, in
 // Copy a head intermediate of the LAST run (first B frames) out as NCHW (B, C, 16, 16).
 extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, float* d_out, void* stream) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (!name || !d_out || B < 1 || B > c->reserved) return set_err(FEAR_EINVAL, "bad argument");
   const float* src = nullptr;
   int ch = kFeatC;
@@ -1187,6 +1069,7 @@ extern "C" int fear_debug_head_tensor(FearContext* c, const char* name, int B, f
 extern "C" int fear_set_option(FearContext* c, const char* key, const char* value) {
   if (!key || !value) return set_err(FEAR_EINVAL, "null option");
   Options& o = c ? c->opt : g_default_options;
+  if (c) c->generation++;
   if (!strcmp(key, "pdl")) {  // process-wide: programmatic dependent launch for the TMA / tcgen05 kernels
     tc::pdl_enabled() = atoi(value) != 0;
     return 0;
@@ -1195,24 +1078,12 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     o.fuse_dwpw = atoi(value) & 3;  // bit 0: 16x16-stage backbone blocks, bit 1: the head's SepConvs
     return 0;
   }
-  if (!strcmp(key, "small_const")) {
-    o.small_const = atoi(value) != 0;
-    return 0;
-  }
   if (!strcmp(key, "fuse_stem")) {
     o.fuse_stem = atoi(value) != 0;
     return 0;
   }
-  if (!strcmp(key, "dw_wide")) {
-    o.dw_wide = atoi(value) != 0;
-    return 0;
-  }
-  if (!strcmp(key, "fuse")) {
-    o.fuse = atoi(value) != 0;
-    return 0;
-  }
-  if (!strcmp(key, "early_sub")) {
-    o.early_sub = atoi(value);
+  if (!strcmp(key, "fuse_irf")) {
+    o.fuse_irf = atoi(value) != 0;
     return 0;
   }
   if (!strcmp(key, "dw")) {
@@ -1220,19 +1091,15 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     else if (!strcmp(value, "strip")) o.dw = 1;
     else if (!strcmp(value, "roll")) o.dw = 2;
     else if (!strcmp(value, "auto")) o.dw = 3;  // measured best per shape: TMA pipeline where it applies, else rolling window (3x3 s1) / register strip
-    else if (!strcmp(value, "tile")) o.dw = 4;
-    else if (!strcmp(value, "blocked")) o.dw = 5;
     else if (!strcmp(value, "tma")) o.dw = 6;
-    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tile | blocked | tma | auto)", value);
+    else return set_err(FEAR_EINVAL, "unknown depthwise implementation '%s' (pixel | strip | roll | tma | auto)", value);
     return 0;
   }
   int impl;
   if (!strcmp(value, "ffma")) impl = IMPL_FFMA;
   else if (!strcmp(value, "tcgen05")) impl = IMPL_TC;
-  else if (!strcmp(value, "tcgen05ts")) impl = IMPL_TS;
-  else if (!strcmp(value, "tcgen05v2")) impl = IMPL_TC2;
   else if (!strcmp(value, "auto")) impl = -1;
-  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (auto | ffma | tcgen05 | tcgen05ts)", value);
+  else return set_err(FEAR_EINVAL, "unknown implementation '%s' (auto | ffma | tcgen05)", value);
   if (impl > IMPL_FFMA && !tc::available()) return set_err(FEAR_EINVAL, "tcgen05 kernels not available in this build");
   if (!strcmp(key, "corr")) o.corr = impl;
   else if (!strcmp(key, "pw")) o.pw = impl;
@@ -1241,9 +1108,11 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
 }
 
 extern "C" int64_t fear_launch_count(const FearContext* c) { return c ? c->launches : 0; }
+extern "C" int64_t fear_generation(const FearContext* c) { return c ? c->generation : -1; }
 
 extern "C" int fear_profile(FearContext* c, int enable) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (enable && c->events.empty()) {
     c->events.resize(8192);
     for (auto& ev : c->events) {
@@ -1262,6 +1131,7 @@ extern "C" int fear_profile(FearContext* c, int enable) {
 
 extern "C" int fear_stage_ms(FearContext* c, int i, float* ms, int64_t* launches) {
   FEAR_TRY(check_ctx(c));
+  DeviceGuard guard(c->device);
   if (i < 0 || i >= ST_COUNT) return set_err(FEAR_EINVAL, "stage index out of range");
   if (c->events_used) {
     CUDA_TRY(cudaDeviceSynchronize());

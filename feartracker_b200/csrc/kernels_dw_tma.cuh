@@ -25,7 +25,6 @@ struct DwTmaParams {
   int Ho, Wo;
   int tiles_x, tiles_y, cblocks;
   int num_tiles;
-  int exp_mode;  // PERF EXPERIMENTS ONLY (wrong results): 1 = no compute, 2 = no TMA waits, 3 = no stores
 };
 
 constexpr int kDwCB = 32;           // channels per tile
@@ -85,7 +84,6 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
 
   // One 4-D box (+ weight slab + biases) per tile, all completing on full[stage].
   auto issue_tile = [&](int tile, int stage) {
-    if (p.exp_mode == 2) return;
     const int cb = tile % p.cblocks;
     int rest = tile / p.cblocks;
     const int tx = rest % p.tiles_x;
@@ -120,13 +118,13 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const int ty = rest % p.tiles_y;
     const int b = rest / p.tiles_y;
     const int c4 = cb * (kDwCB / 4) + cg;
-    if (p.exp_mode != 2) mbar_wait(&full[s], ph);
+    mbar_wait(&full[s], ph);
     const F4* in4 = reinterpret_cast<const F4*>(smem + s * T::kStageBytes);
     const F4* w4 = reinterpret_cast<const F4*>(smem + s * T::kStageBytes + T::kInBytes);
     const F4* b4p = reinterpret_cast<const F4*>(smem + s * T::kStageBytes + T::kInBytes + T::kWBytes);
 
 #pragma unroll 1
-    for (int pos = gwarp * 4 + (lane >> 3); pos < (p.exp_mode == 1 ? 0 : NPOS); pos += kDwGroupWarps * 4) {
+    for (int pos = gwarp * 4 + (lane >> 3); pos < NPOS; pos += kDwGroupWarps * 4) {
       const int px = pos % PX, py = pos / PX;
       const int ox_l = px * TX, oy_l = py * TY;
       F4 acc[TY][TX];
@@ -163,7 +161,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
           }
         }
       }
-      if (c4 < p.C4 && (p.exp_mode != 3 || acc[0][0].lo == 123456ull)) {
+      if (c4 < p.C4) {
         float4* o = reinterpret_cast<float4*>(p.out) +
                     (((long long)b * p.Ho + ty * TH + oy_l) * p.Wo + tx * TW + ox_l) * p.C4 + c4;
 #pragma unroll
@@ -187,7 +185,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
       if (gwarp == 0) {  // refill this stage with the tile STAGES iterations ahead once the whole group has left it
         const int next = tile + STAGES * gridDim.x;
         if (next < p.num_tiles) {
-          if (p.exp_mode != 2) mbar_wait(&empty[s], ph);
+          mbar_wait(&empty[s], ph);
           issue_tile(next, s);
         }
       }
@@ -205,10 +203,8 @@ inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, cons
   if (Ho % TH || Wo % TW || C % 4) return 1;
   auto kern = dw_tma_kernel<K, S, TH, TW, TX, TY, STAGES, GROUPS, RELU, BIAS>;
   constexpr int smem = dw_tma_smem_bytes<K, S, TH, TW, STAGES>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (attr_needed(reinterpret_cast<const void*>(kern))) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
-    attr_done = true;
   }
   CUtensorMap tmIn, tmW, tmB;
   int r = make_tmap_nhwc(&tmIn, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)C, kDwCB, T::IW, T::IH);
@@ -230,8 +226,6 @@ inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, cons
   p.tiles_y = Ho / TH;
   p.cblocks = (C + kDwCB - 1) / kDwCB;
   p.num_tiles = B * p.tiles_x * p.tiles_y * p.cblocks;
-  p.exp_mode = 0;
-  if (const char* e = getenv("FEAR_EXP_DW")) p.exp_mode = atoi(e);
   int grid = num_sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
   if (launch_pdl(kern, dim3(grid), dim3(GROUPS * kDwGroupWarps * 32), (size_t)smem, s, tmIn, tmW, tmB, p) != cudaSuccess) return -31;

@@ -196,82 +196,6 @@ __global__ void __launch_bounds__(TX >= 16 ? 128 : 256) dw_conv_strip_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------
-// Register-strip depthwise conv with an L1-friendly thread layout.  Same arithmetic as
-// dw_conv_strip_kernel, but a CTA now owns a compact patch -- 8 channel groups (32 channels) x 4 adjacent
-// strips x 8 output rows -- instead of 256 consecutive channel groups of one strip.  Neighbouring rows and
-// strips share (K-1)/K of their inputs, and with this layout those re-reads hit L1 (ncu showed the flat
-// layout pulling ~2.5x the algorithmic bytes through L2 on the 5x5 layers).  A warp covers 8 channel
-// groups of 4 strips in one row => each load instruction touches four 128-byte segments.
-// ------------------------------------------------------------------------------------------
-template <int K, int S, int TX, bool RELU, bool BIAS>
-__global__ void __launch_bounds__(256) dw_conv_strip_blocked_kernel(const float4* __restrict__ in,
-                                                                    const float4* __restrict__ w,
-                                                                    const float4* __restrict__ bias,
-                                                                    float4* __restrict__ out, int B, int H, int W,
-                                                                    int C4) {
-  const int Ho = H / S, Wo = W / S;
-  const int strips = Wo / TX;
-  const int sgroups = (strips + 3) / 4, rgroups = (Ho + 7) / 8, cgroups = (C4 + 7) / 8;
-  int t = blockIdx.x;
-  const int cg = t % cgroups;
-  t /= cgroups;
-  const int sg = t % sgroups;
-  t /= sgroups;
-  const int rg = t % rgroups;
-  const int b = t / rgroups;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int c4 = cg * 8 + (lane & 7);
-  const int sx = sg * 4 + (lane >> 3);
-  const int oy = rg * 8 + wrp;
-  if (c4 >= C4 || sx >= strips || oy >= Ho) return;
-  constexpr int P = K / 2;
-  constexpr int NIN = (TX - 1) * S + K;
-  const int ox0 = sx * TX;
-  const int ix0 = ox0 * S - P;
-  float4 acc[TX];
-  const float4 b4 = BIAS ? __ldg(bias + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < TX; ++i) acc[i] = b4;
-  const float4* inb = in + (long long)b * H * W * C4 + c4;
-#pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-    const int iy = oy * S - P + ky;
-    if (iy < 0 || iy >= H) continue;
-    const float4* row = inb + (long long)iy * W * C4;
-    float4 v[NIN];
-#pragma unroll
-    for (int i = 0; i < NIN; ++i) {
-      const int ix = ix0 + i;
-      v[i] = (ix >= 0 && ix < W) ? __ldg(row + (long long)ix * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const float4 k = __ldg(w + (ky * K + kx) * C4 + c4);
-#pragma unroll
-      for (int i = 0; i < TX; ++i) {
-        const float4 x = v[i * S + kx];
-        acc[i].x = fmaf(x.x, k.x, acc[i].x);
-        acc[i].y = fmaf(x.y, k.y, acc[i].y);
-        acc[i].z = fmaf(x.z, k.z, acc[i].z);
-        acc[i].w = fmaf(x.w, k.w, acc[i].w);
-      }
-    }
-  }
-  float4* o = out + (((long long)b * Ho + oy) * Wo + ox0) * C4 + c4;
-#pragma unroll
-  for (int i = 0; i < TX; ++i) {
-    float4 r = acc[i];
-    if (RELU) {
-      r.x = fmaxf(r.x, 0.f);
-      r.y = fmaxf(r.y, 0.f);
-      r.z = fmaxf(r.z, 0.f);
-      r.w = fmaxf(r.w, 0.f);
-    }
-    o[(long long)i * C4] = r;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Depthwise KxK conv, rolling-window version.  One thread owns (4 channels, TX output columns) and
 // walks ROWS output rows top to bottom: all K*K weights live in registers, every input row segment
 // is loaded ONCE and scattered into a ring of ceil(K/S) live output-row accumulators, so a 5x5 conv
@@ -455,295 +379,42 @@ __global__ void __launch_bounds__(256) gemm_nt_ffma_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// Depthwise KxK stride-1 conv, shared-memory tiled: one CTA = one frame x 16x16 output tile x 32-channel
-// slab.  The (16+K-1)^2 x 32-channel input patch is staged once in shared memory (coalesced 128-byte
-// rows, zero halo), so every input value is fetched from L2/HBM exactly once per tile instead of being
-// re-requested through L1 by up to K*K neighbouring threads (the strip kernel moves ~2.5x the algorithmic
-// bytes through L2 on the 16x16 stage).  Each thread owns 4 channels x 8 consecutive pixels of a row;
-// per kernel row it reads 8+K-1 inputs and K weights from shared memory for 8*K FMA4.
-// Accumulation order per output is the same as in the other depthwise kernels (bit-identical results).
+// Pixel-wise correlation straight on the reference's layouts (MobileCorrelation.forward, blocks.py:121-123):
+//   out[b, 256 + k, p] = sum_c z[b, c, k] * x[b, c, p],  z (Bz,256,64), x (B,256,256), out (B,320,256).
+// Compatibility kernel of the workspace-free C entry point fear_corr_concat_f32; the hot path runs
+// tc::corr_tc_kernel on the channels-last concat buffer instead.  grid (4, B), 256 threads: 64 pixels x 4 groups
+// of 16 template cells, the template streamed through shared memory in 64-channel slices.
 // ------------------------------------------------------------------------------------------
-template <int K, bool RELU, bool BIAS>
-__global__ void __launch_bounds__(256, 2) dw_conv_tile_kernel(const float4* __restrict__ in, const float4* __restrict__ w,
-                                                           const float4* __restrict__ bias, float4* __restrict__ out,
-                                                           int H, int W, int C4) {
-  constexpr int T = 16, TX = 8, P = K / 2, IT = T + K - 1, CS4 = 8;  // 32-channel slab = 8 float4
-  extern __shared__ __align__(16) float4 dw_tile_smem[];
-  float4* sIn = dw_tile_smem;              // [IT * IT][CS4]
-  float4* sW = sIn + IT * IT * CS4;        // [K * K][CS4]
-  const int tid = threadIdx.x;
-  const int slabs = C4 / CS4;
-  const int tiles_x = W / T, tiles_y = H / T;
-  int t = blockIdx.x;
-  const int slab = t % slabs;
-  t /= slabs;
-  const int tx = t % tiles_x;
-  t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int c40 = slab * CS4;
-  const int y0 = ty * T - P, x0 = tx * T - P;
-  const float4* inb = in + (long long)b * H * W * C4 + c40;
-  for (int i = tid; i < IT * IT * CS4; i += 256) {
-    const int q = i % CS4, p = i / CS4;
-    const int iy = y0 + p / IT, ix = x0 + p % IT;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(inb + ((long long)iy * W + ix) * C4 + q);
-    sIn[i] = v;
-  }
-  for (int i = tid; i < K * K * CS4; i += 256) sW[i] = __ldg(w + (i / CS4) * C4 + c40 + (i % CS4));
-  __syncthreads();
-
-  const int q = tid % CS4;           // channel group inside the slab
-  const int strip = tid / CS4;       // 32 strips: 16 rows x 2 half-rows
-  const int oy = strip >> 1, ox0 = (strip & 1) * TX;
-  const float4 b4 = BIAS ? __ldg(bias + c40 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 acc[TX];
+__global__ void __launch_bounds__(256) corr_nchw_ffma_kernel(const float* __restrict__ z, long long z_stride,
+                                                             const float* __restrict__ x, float* __restrict__ out) {
+  __shared__ float sz[64 * 64];  // [channel within the slice][template cell]
+  const int b = blockIdx.y, p = blockIdx.x * 64 + (threadIdx.x & 63), kq = threadIdx.x >> 6;
+  const float* zb = z + (long long)b * z_stride;
+  const float* xb = x + (long long)b * 256 * 256;
+  float acc[16];
 #pragma unroll
-  for (int i = 0; i < TX; ++i) acc[i] = b4;
-#pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-    float4 v[TX + K - 1];
-    const float4* row = sIn + ((oy + ky) * IT + ox0) * CS4 + q;
-#pragma unroll
-    for (int i = 0; i < TX + K - 1; ++i) v[i] = row[i * CS4];
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const float4 k = sW[(ky * K + kx) * CS4 + q];
-#pragma unroll
-      for (int i = 0; i < TX; ++i) {
-        acc[i].x = fmaf(v[i + kx].x, k.x, acc[i].x);
-        acc[i].y = fmaf(v[i + kx].y, k.y, acc[i].y);
-        acc[i].z = fmaf(v[i + kx].z, k.z, acc[i].z);
-        acc[i].w = fmaf(v[i + kx].w, k.w, acc[i].w);
-      }
-    }
-  }
-  float4* o = out + (long long)b * H * W * C4 + ((long long)(ty * T + oy) * W + tx * T + ox0) * C4 + c40 + q;
-#pragma unroll
-  for (int i = 0; i < TX; ++i) {
-    float4 r = acc[i];
-    if (RELU) {
-      r.x = fmaxf(r.x, 0.f);
-      r.y = fmaxf(r.y, 0.f);
-      r.z = fmaxf(r.z, 0.f);
-      r.w = fmaxf(r.w, 0.f);
-    }
-    o[(long long)i * C4] = r;
-  }
-}
-
-template <int K>
-constexpr int dw_tile_smem_bytes() {
-  return 16 * ((16 + K - 1) * (16 + K - 1) * 8 + K * K * 8);
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused inverted-residual front half for the stride-2 blocks (xif2_0, xif3_0, xif4_0):
-//     D = ReLU(dw_KxK_s2(ReLU(X * W1^T + b1)) + b2)
-// The 6x-expanded tensor E = ReLU(X*W1^T + b1) (1.6 GB per 256-frame step for xif2_0 alone) never leaves
-// the SM: each CTA takes a TH x TW tile of OUTPUT pixels, stages the (2TH+K-2) x (2TW+K-2) input patch of X,
-// expands it into shared memory with CUDA cores (Cin is only 16..32 here, so this is ~1 FLOP per byte of
-// the unfused traffic), then runs the depthwise stride-2 window over the resident tile and writes D.
-// Pixels of the patch that fall outside the image are forced to 0 (the depthwise conv zero-pads E, and
-// E(0-input) = ReLU(b1) != 0).
-// ------------------------------------------------------------------------------------------
-template <int CIN, int MID, int MSL, int K, int TH, int TW, int THREADS>
-__global__ void __launch_bounds__(THREADS) fused_expand_dw_s2_kernel(
-    const float* __restrict__ X, const float* __restrict__ w1, const float* __restrict__ b1,
-    const float* __restrict__ wd, const float* __restrict__ bd, float* __restrict__ D, int H, int W) {
-  // MSL = channels of the expanded tensor resident at a time (MID / MSL passes over the same input patch):
-  // a smaller slice buys a larger spatial tile, i.e. less halo recomputation for the 5x5 blocks.
-  static_assert(MID % MSL == 0 && MSL % 4 == 0 && CIN % 4 == 0, "channel slicing");
-  constexpr int P = K / 2;
-  constexpr int IH = 2 * TH + K - 2, IW = 2 * TW + K - 2, NPIX = IH * IW;
-  constexpr int C4 = MSL / 4, K4 = CIN / 4;
-  extern __shared__ __align__(16) float fsm[];
-  float* sX = fsm;                        // [NPIX][CIN]
-  float* sW1 = sX + NPIX * CIN;           // [CIN][MID]  (transposed: channel-contiguous per k)
-  float* sB1 = sW1 + CIN * MID;           // [MID]
-  float* sWd = sB1 + MID;                 // [K*K][MID]
-  float* sBd = sWd + K * K * MID;         // [MID]
-  float* sE = sBd + MID;                  // [NPIX][MSL]
-  const int tid = threadIdx.x;
-  const int Ho = H / 2, Wo = W / 2;
-  const int tiles_x = Wo / TW, tiles_y = Ho / TH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x;
-  t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int oy0 = ty * TH, ox0 = tx * TW;
-  const int iy0 = 2 * oy0 - P, ix0 = 2 * ox0 - P;
-
-  // ---- stage weights and the input patch --------------------------------------------------
-  for (int i = tid; i < CIN * MID; i += THREADS) {
-    const int o = i / CIN, k = i - o * CIN;  // w1 is [MID][CIN]
-    sW1[k * MID + o] = __ldg(w1 + i);
-  }
-  for (int i = tid; i < MID; i += THREADS) {
-    sB1[i] = __ldg(b1 + i);
-    sBd[i] = __ldg(bd + i);
-  }
-  for (int i = tid; i < K * K * MID; i += THREADS) sWd[i] = __ldg(wd + i);
-  const float* Xb = X + (long long)b * H * W * CIN;
-  for (int i = tid; i < NPIX * K4; i += THREADS) {
-    const int p = i / K4, q = i - p * K4;
-    const int iy = iy0 + p / IW, ix = ix0 + p % IW;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(Xb + ((long long)iy * W + ix) * CIN) + q);
-    reinterpret_cast<float4*>(sX)[i] = v;
-  }
-  __syncthreads();
-
-  float* Db = D + (long long)b * Ho * Wo * MID;
-  constexpr int PG = (NPIX + 3) / 4;
-#pragma unroll 1
-  for (int m0 = 0; m0 < MID; m0 += MSL) {
-    // ---- expand: E[p][c] = ReLU(b1[c] + sum_k X[p][k] W1[c][k]), 4 pixels x 4 channels per work item ----
-    for (int u = tid; u < PG * C4; u += THREADS) {
-      const int c4 = u % C4, pg = u / C4;
-      const int ch = m0 + 4 * c4;
-      const float4 bb = *reinterpret_cast<const float4*>(sB1 + ch);
-      float4 acc[4] = {bb, bb, bb, bb};
-#pragma unroll
-      for (int kq = 0; kq < K4; ++kq) {
-        float4 xv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int p = pg * 4 + j;
-          xv[j] = (p < NPIX) ? *reinterpret_cast<const float4*>(sX + p * CIN + 4 * kq) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float4 wv = *reinterpret_cast<const float4*>(sW1 + (4 * kq + kk) * MID + ch);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xs = kk == 0 ? xv[j].x : kk == 1 ? xv[j].y : kk == 2 ? xv[j].z : xv[j].w;
-            acc[j].x = fmaf(xs, wv.x, acc[j].x);
-            acc[j].y = fmaf(xs, wv.y, acc[j].y);
-            acc[j].z = fmaf(xs, wv.z, acc[j].z);
-            acc[j].w = fmaf(xs, wv.w, acc[j].w);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = pg * 4 + j;
-        if (p < NPIX) {
-          const int iy = iy0 + p / IW, ix = ix0 + p % IW;
-          const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
-          float4 e = make_float4(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f), fmaxf(acc[j].z, 0.f), fmaxf(acc[j].w, 0.f));
-          if (!inside) e = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(sE + p * MSL + 4 * c4) = e;
-        }
-      }
-    }
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < 256; c0 += 64) {
     __syncthreads();
-
-    // ---- depthwise KxK stride 2 over the resident slice -------------------------------------
-    for (int u = tid; u < TH * TW * C4; u += THREADS) {
-      const int c4 = u % C4, op = u / C4;
-      const int oy = op / TW, ox = op % TW;
-      const int ch = m0 + 4 * c4;
-      float4 acc = *reinterpret_cast<const float4*>(sBd + ch);
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) sz[i] = __ldg(zb + c0 * 64 + i);
+    __syncthreads();
+    for (int cc = 0; cc < 64; ++cc) {
+      const float xv = __ldg(xb + (c0 + cc) * 256 + p);
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const float4 e = *reinterpret_cast<const float4*>(sE + ((2 * oy + ky) * IW + 2 * ox + kx) * MSL + 4 * c4);
-          const float4 k = *reinterpret_cast<const float4*>(sWd + (ky * K + kx) * MID + ch);
-          acc.x = fmaf(e.x, k.x, acc.x);
-          acc.y = fmaf(e.y, k.y, acc.y);
-          acc.z = fmaf(e.z, k.z, acc.z);
-          acc.w = fmaf(e.w, k.w, acc.w);
-        }
-      acc.x = fmaxf(acc.x, 0.f);
-      acc.y = fmaxf(acc.y, 0.f);
-      acc.z = fmaxf(acc.z, 0.f);
-      acc.w = fmaxf(acc.w, 0.f);
-      *reinterpret_cast<float4*>(Db + ((long long)(oy0 + oy) * Wo + ox0 + ox) * MID + ch) = acc;
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(sz[cc * 64 + kq * 16 + j], xv, acc[j]);
     }
-    __syncthreads();  // the slice buffer is rewritten by the next pass
   }
-}
-
-template <int CIN, int MID, int MSL, int K, int TH, int TW>
-constexpr int fused_expand_dw_smem_bytes() {
-  constexpr int NPIX = (2 * TH + K - 2) * (2 * TW + K - 2);
-  return 4 * (NPIX * CIN + CIN * MID + MID + K * K * MID + MID + NPIX * MSL);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[((long long)b * 320 + 256 + kq * 16 + j) * 256 + p] = acc[j];
 }
 
 // ------------------------------------------------------------------------------------------
-// Tiny 1x1 convs (Cin, Cout <= 32: xif1_0.pwl 16->16, xif2_2/2_3.pwl 24->24) are pure streaming:
-// ~1 FLOP per byte, millions of pixels.  A tensor-core tile pipeline only adds per-tile latency there
-// (measured: 585 us vs the 125 us HBM time), so these run one pixel per thread on CUDA cores with the
-// [Cin][Cout] weights broadcast from shared memory.   out = act(x * W^T + b (+ residual)).
+// Tiny 1x1 convs (xif1_0.pwl 16->16, xif2_2/2_3.pwl 24->24) are pure streaming: ~1 FLOP per byte, millions of
+// pixels.  A tensor-core tile pipeline only adds per-tile latency there, so these run one pixel per thread on CUDA
+// cores with the [Cin][Cout] weights passed BY VALUE (kernel parameter = constant bank): every FFMA takes its weight
+// as a uniform-register / constant operand.  (A broadcast LDS costs one LSU wavefront per 4 bytes even when all
+// lanes read the same address, which made a shared-memory version LSU-bound.)   out = act(x * W^T + b (+ residual)).
 // ------------------------------------------------------------------------------------------
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) pw_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, const float* __restrict__ res,
-                                                       float* __restrict__ out, long long M, int relu) {
-  __shared__ __align__(16) float sw[CIN * COUT];  // [k][o]
-  __shared__ __align__(16) float sb[COUT];
-  for (int i = threadIdx.x; i < CIN * COUT; i += blockDim.x) {
-    const int o = i / CIN, k = i - o * CIN;  // global layout [o][k]
-    sw[k * COUT + o] = w[i];
-  }
-  if (threadIdx.x < COUT) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float xin[CIN];
-  const float4* xp = reinterpret_cast<const float4*>(x + m * CIN);
-#pragma unroll
-  for (int i = 0; i < CIN / 4; ++i) {
-    const float4 v = __ldg(xp + i);
-    xin[4 * i] = v.x;
-    xin[4 * i + 1] = v.y;
-    xin[4 * i + 2] = v.z;
-    xin[4 * i + 3] = v.w;
-  }
-  float acc[COUT];
-#pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = sb[o];
-#pragma unroll
-  for (int k = 0; k < CIN; ++k) {
-#pragma unroll
-    for (int o4 = 0; o4 < COUT / 4; ++o4) {
-      const float4 wv = *reinterpret_cast<const float4*>(&sw[k * COUT + 4 * o4]);
-      acc[4 * o4] = fmaf(xin[k], wv.x, acc[4 * o4]);
-      acc[4 * o4 + 1] = fmaf(xin[k], wv.y, acc[4 * o4 + 1]);
-      acc[4 * o4 + 2] = fmaf(xin[k], wv.z, acc[4 * o4 + 2]);
-      acc[4 * o4 + 3] = fmaf(xin[k], wv.w, acc[4 * o4 + 3]);
-    }
-  }
-  float4* op = reinterpret_cast<float4*>(out + m * COUT);
-  const float4* rp = res ? reinterpret_cast<const float4*>(res + m * COUT) : nullptr;
-#pragma unroll
-  for (int o4 = 0; o4 < COUT / 4; ++o4) {
-    float4 r = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
-    if (rp) {
-      const float4 q = __ldg(rp + o4);
-      r.x += q.x;
-      r.y += q.y;
-      r.z += q.z;
-      r.w += q.w;
-    }
-    if (relu) {
-      r.x = fmaxf(r.x, 0.f);
-      r.y = fmaxf(r.y, 0.f);
-      r.z = fmaxf(r.z, 0.f);
-      r.w = fmaxf(r.w, 0.f);
-    }
-    op[o4] = r;
-  }
-}
-
-// Same layer with the weights passed BY VALUE (kernel parameter = constant bank): every FFMA takes its weight as a
-// uniform-register / constant operand instead of a shared-memory broadcast.  An LDS costs one LSU wavefront per
-// 4 bytes even when all lanes read the same address, which made the smem version LSU-bound (CIN*COUT/4 LDS.128
-// per pixel against CIN*COUT FMAs).  Same accumulation order => bit-identical results.
 template <int CIN, int COUT>
 struct PwSmallWeights {
   float w[CIN * COUT];  // [k][o]

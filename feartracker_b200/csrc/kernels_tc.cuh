@@ -44,9 +44,7 @@ constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) col
 
 __global__ void __launch_bounds__(kCorrThreads, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               float* __restrict__ cat, int num_frames, int z_mod, int exp_mode) {
-  // exp_mode (PERF EXPERIMENTS ONLY, results wrong): 1 = skip the split arithmetic, 2 = one MMA per K-step,
-  // 4 = skip the epilogue stores.  0 in production.
+               float* __restrict__ cat, int num_frames, int z_mod) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes);
@@ -136,14 +134,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
             // so the (truncating) tensor-core adder rounds the big sum 3x less often
-            if (exp_mode & 2) {
-              mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            } else {
-              // the hi and lo template tiles are adjacent in smem, so ONE N=128 MMA yields [x_hi*z_hi | x_hi*z_lo]
-              // in the adjacent (main | correction) accumulators and x_hi is read from smem once, not twice
-              mma_tf32_ss(d, dah, dbh, idesc2, (c | j) != 0);
-              mma_tf32_ss(d + 64, dal, dbh, idesc, 1);
-            }
+            // the hi and lo template tiles are adjacent in smem, so ONE N=128 MMA yields [x_hi*z_hi | x_hi*z_lo]
+            // in the adjacent (main | correction) accumulators and x_hi is read from smem once, not twice
+            mma_tf32_ss(d, dah, dbh, idesc2, (c | j) != 0);
+            mma_tf32_ss(d + 64, dal, dbh, idesc, 1);
           }
           tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
           if (++stage == kCorrStages) {
@@ -166,7 +160,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[stage], phase);
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
         float4* al = reinterpret_cast<float4*>(a_lo(stage));
-        if (!(exp_mode & 1)) {
+        {
 #pragma unroll
           for (int i = 0; i < kCorrABytes / 16 / kCorrSplitThreads; ++i) {
             const float4 v = ah[ts + i * kCorrSplitThreads];
@@ -237,233 +231,6 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int rb = 0; rb < 4; ++rb) {
           const int rl = rb * 8 + (lane >> 2);
-          if (!(exp_mode & 4))
-            *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
-        }
-        __syncwarp();
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kCorrTmemCols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// corr_tc2_kernel -- correlation with DECOUPLED landing and operand rings.
-//
-// The ablation of corr_tc_kernel (profiles/r1_corr_ablation.txt) showed its 4-stage ring is latency bound: a
-// stage is held from the TMA issue until the MMAs that read it complete, so only part of the 192 KB of smem is
-// ever "in flight" towards HBM.  Here the TMA lands raw x tiles in a deep ring of pure landing buffers
-// (7 x 16 KB); the split warps copy each tile into a 2-slot operand ring as (hi, lo) and release the landing
-// slot at once; the tensor core reads only the operand ring.  The template tiles come pre-split (hi / lo planes
-// produced once per template by split_hi_lo_kernel) through their own 2-slot ring fed by a second producer warp,
-// so neither ring can stall the other.  Everything else (TMEM accumulators, epilogue) is as in corr_tc_kernel.
-// ------------------------------------------------------------------------------------------
-constexpr int kC2Landing = 3;   // raw landing slots (TMA in flight)
-constexpr int kC2Ops = 3;       // (hi, lo) operand slots between the split warps and the tensor core
-constexpr int kC2B = 4;         // template (hi, lo) tile slots
-constexpr int kC2Threads = 480;  // A producer, MMA, 8 split warps, 4 epilogue warps, B producer
-constexpr int kC2SmemBytes = kC2Landing * kCorrABytes + kC2Ops * 2 * kCorrABytes + kC2B * 2 * kCorrBBytes + 1024 /*align*/ +
-                             512 /*barriers*/ + 8192 /*epilogue*/;
-
-__global__ void __launch_bounds__(kC2Threads, 1)
-corr_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                const __grid_constant__ CUtensorMap tmBl, float* __restrict__ cat, int num_frames, int z_mod) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
-  uint8_t* landing = smem;                                   // [7][16 KB] raw x tiles
-  uint8_t* opring = landing + kC2Landing * kCorrABytes;      // [2][hi 16 KB | lo 16 KB]
-  uint8_t* bring = opring + kC2Ops * 2 * kCorrABytes;        // [2][hi 8 KB | lo 8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + kC2B * 2 * kCorrBBytes);
-  uint64_t* land_full = bars;            // [7]
-  uint64_t* land_empty = bars + 8;       // [7] count 8 (split warps)
-  uint64_t* op_full = bars + 16;         // [kC2Ops] count 8
-  uint64_t* op_empty = bars + 24;        // [kC2Ops] commit
-  uint64_t* b_full = bars + 32;          // [kC2B]
-  uint64_t* b_empty = bars + 40;         // [kC2B] commit
-  uint64_t* acc_full = bars + 48;        // [2]
-  uint64_t* acc_empty = bars + 50;       // [2] count 4
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 52);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 512;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = num_frames * 2;
-  constexpr int kChunks = 256 / kCorrChunk;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmBh);
-    prefetch_tmap(&tmBl);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, kCorrTmemCols);
-    tmem_relinquish();
-  }
-  if (threadIdx.x == 64) {
-    for (int s = 0; s < kC2Landing; ++s) {
-      mbar_init(&land_full[s], 1);
-      mbar_init(&land_empty[s], 8);
-    }
-    for (int a = 0; a < kC2Ops; ++a) {
-      mbar_init(&op_full[a], 8);
-      mbar_init(&op_empty[a], 1);
-    }
-    for (int a = 0; a < kC2B; ++a) {
-      mbar_init(&b_full[a], 1);
-      mbar_init(&b_empty[a], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
-    }
-    fence_mbar_init();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ---- x producer: keeps up to 7 raw tiles (112 KB) in flight -------------------------------------
-    if (lane == 0) {
-      int sl = 0;
-      uint32_t pl = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int arow = (t >> 1) * 256 + (t & 1) * 128;
-        for (int c = 0; c < kChunks; ++c) {
-          mbar_wait(&land_empty[sl], pl ^ 1);
-          mbar_arrive_expect_tx(&land_full[sl], kCorrABytes);
-          tma_load_2d(landing + sl * kCorrABytes, &tmA, &land_full[sl], c * kCorrChunk, arow);
-          if (++sl == kC2Landing) { sl = 0; pl ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 14) {
-    // ---- template producer: pre-split (hi, lo) tiles, L2 resident -----------------------------------
-    if (lane == 0) {
-      int sb = 0;
-      uint32_t pb = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int frame = t >> 1;
-        const int brow = z_mod ? (frame % z_mod) * 64 : 0;
-        for (int c = 0; c < kChunks; ++c) {
-          mbar_wait(&b_empty[sb], pb ^ 1);
-          mbar_arrive_expect_tx(&b_full[sb], 2 * kCorrBBytes);
-          tma_load_2d(bring + sb * 2 * kCorrBBytes, &tmBh, &b_full[sb], c * kCorrChunk, brow);
-          tma_load_2d(bring + sb * 2 * kCorrBBytes + kCorrBBytes, &tmBl, &b_full[sb], c * kCorrChunk, brow);
-          if (++sb == kC2B) { sb = 0; pb ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---- MMA issuer -----------------------------------------------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
-      int so = 0, sb = 0, acc = 0;
-      uint32_t po = 0, pb = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * 128;
-        for (int c = 0; c < kChunks; ++c) {
-          mbar_wait(&op_full[so], po);
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t ah = smem_u32(opring + so * 2 * kCorrABytes), al = ah + kCorrABytes;
-          const uint32_t bh = smem_u32(bring + sb * 2 * kCorrBBytes), bl = bh + kCorrBBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
-            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
-            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + 64, dal, dbh, idesc, (c | j) != 0);
-            mma_tf32_ss(d + 64, dah, dbl, idesc, 1);
-          }
-          tc_commit(&op_empty[so]);
-          tc_commit(&b_empty[sb]);
-          if (++so == kC2Ops) { so = 0; po ^= 1; }
-          if (++sb == kC2B) { sb = 0; pb ^= 1; }
-        }
-        tc_commit(&acc_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else if (warp < 10) {
-    // ---- split: landing slot -> operand slot (hi copy + lo), landing slot released immediately -----------
-    const int ts = threadIdx.x - 64;
-    int sl = 0, so = 0;
-    uint32_t pl = 0, po = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int c = 0; c < kChunks; ++c) {
-        mbar_wait(&land_full[sl], pl);
-        mbar_wait(&op_empty[so], po ^ 1);
-        const float4* src = reinterpret_cast<const float4*>(landing + sl * kCorrABytes);
-        float4* dh = reinterpret_cast<float4*>(opring + so * 2 * kCorrABytes);
-        float4* dl = reinterpret_cast<float4*>(opring + so * 2 * kCorrABytes + kCorrABytes);
-#pragma unroll
-        for (int i = 0; i < kCorrABytes / 16 / 256; ++i) {
-          const float4 v = src[ts + i * 256];
-          float4 h, l;
-          split_tf32_trunc(v.x, h.x, l.x);
-          split_tf32_trunc(v.y, h.y, l.y);
-          split_tf32_trunc(v.z, h.z, l.z);
-          split_tf32_trunc(v.w, h.w, l.w);
-          dh[ts + i * 256] = v;  // raw word = hi operand (kind::tf32 ignores the low 13 bits)
-          dl[ts + i * 256] = l;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&land_empty[sl]);
-          mbar_arrive(&op_full[so]);
-        }
-        if (++sl == kC2Landing) { sl = 0; pl ^= 1; }
-        if (++so == kC2Ops) { so = 0; po ^= 1; }
-      }
-    }
-  } else if (warp < 14) {
-    // ---- epilogue (as in corr_tc_kernel) -----------------------------------------------------------------
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int frame = t >> 1, half = t & 1;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16);
-      const long long row0 = (long long)frame * 256 + half * 128 + q * 32;
-#pragma unroll
-      for (int g = 0; g < 64; g += 16) {
-        uint32_t m[16], sm[16];
-        tmem_ld_32x16(taddr + g, m);
-        tmem_ld_32x16(taddr + 64 + g, sm);
-        tmem_ld_wait();
-        if (g == 48) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
-              make_float4(__uint_as_float(m[4 * j]) + __uint_as_float(sm[4 * j]),
-                          __uint_as_float(m[4 * j + 1]) + __uint_as_float(sm[4 * j + 1]),
-                          __uint_as_float(m[4 * j + 2]) + __uint_as_float(sm[4 * j + 2]),
-                          __uint_as_float(m[4 * j + 3]) + __uint_as_float(sm[4 * j + 3]));
-        __syncwarp();
-        const int j = lane & 3;
-#pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-          const int rl = rb * 8 + (lane >> 2);
           *reinterpret_cast<float4*>(cat + (row0 + rl) * 320 + 256 + g + j * 4) = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
         }
         __syncwarp();
@@ -485,48 +252,41 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // Host side
 // ------------------------------------------------------------------------------------------
 inline int init_pw();
-static int g_num_sms = 0;
-static bool g_tc_ready = false;
 
+// Per-device initialisation (called by fear_init with the device selected).
 inline int init() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return -1;
-  g_num_sms = p.multiProcessorCount;
+  DeviceState& st = dev_state();
+  st.num_sms = p.multiProcessorCount;
+  st.inited = true;
   if (resolve_driver()) return 0;  // tcgen05 path stays unavailable; the FFMA path still works
   if (cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmemBytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   if (init_pw()) return 0;
-  g_tc_ready = true;
+  st.tc_ready = true;
   return 0;
 }
-
-inline bool available() { return g_tc_ready; }
 
 // cat holds `groups` consecutive [B][256][320] buffers (the cls and reg branches of the head): frame f of
 // every group correlates with template f (or template 0 when Bz == 1).  One launch for all groups keeps
 // the persistent grid busy for ~7 tile rounds instead of 3.46, i.e. almost no tail.
 inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int B, int groups) {
-  if (!g_tc_ready) return -20;
+  if (!available()) return -20;
   CUtensorMap tmA, tmB;
   const int frames = B * groups;
   int r;
-  if (getenv("FEAR_EXP_CONTIG"))  // PERF EXPERIMENT ONLY (wrong results): A boxes contiguous in memory
-    r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256 * 10, 32, 32, 128, kCorrChunk);
-  else
-    r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
+  r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
   if (r) return r;
   r = make_tmap_2d(&tmB, zt, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
   if (r) return r;
   const int tiles = frames * 2;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  int exp_mode = 0;
-  if (const char* e = getenv("FEAR_EXP_MODE")) exp_mode = atoi(e);
-  if (launch_pdl(corr_tc_kernel, dim3(grid), dim3(kCorrThreads), kCorrSmemBytes, s, tmA, tmB, cat, frames, Bz == 1 ? 0 : B,
-                 exp_mode) != cudaSuccess)
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (launch_pdl(corr_tc_kernel, dim3(grid), dim3(kCorrThreads), kCorrSmemBytes, s, tmA, tmB, cat, frames, Bz == 1 ? 0 : B) != cudaSuccess)
     return -23;
   return 0;
 }
@@ -996,357 +756,6 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 constexpr int kPwMaxSmem = 232448 - 1024;  // 227 KB opt-in limit minus static/driver slack
 constexpr int kPwTailBytes = 1024 /*barriers*/ + 8 * 2 * 2048 /*epilogue staging*/ + 2048 /*bias*/;
 
-// ------------------------------------------------------------------------------------------
-// gemm_ts_kernel -- second-generation tensor-core GEMM: the activation operand lives in TENSOR MEMORY.
-//
-// Profiling the SS kernels above (profiles/r1_*) showed them bound by shared-memory bandwidth, not by
-// HBM or the tensor pipe: per 32-channel chunk the smem port moved TMA writes + split reads/writes
-// (hi rewritten in place, lo tile written) + three MMAs each re-reading the A tile (~170-190 KB/chunk).
-// Here the convert warps read the raw fp32 A tile from smem ONCE, split it in registers and park
-// (hi, lo) in TMEM with tcgen05.st; the MMAs take A from TMEM ("TS" form) and only the B operand from
-// smem.  A's smem slot is free as soon as it has been read, so the A ring and the B ring have
-// independent depths and more bytes stay in flight.
-//
-//   C[M][ldc] = act(A[M][K] * Bm[g][N][K]^T + bias (+R)),   Bm pre-split into tf32 (hi, lo) planes.
-//   Tile = 128 rows x NT cols.  Group g of a tile selects the B matrix: g = (mt / tiles_per_group) %
-//   group_mod  (1x1 conv: one shared B; correlation: one template per frame, 2 row tiles per frame).
-//
-// TMEM columns: [0,128) two A slots (32 hi + 32 lo each); then `sets` x (main NT | correction NT).
-// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 convert, warps 6-9 epilogue.
-// ------------------------------------------------------------------------------------------
-struct TsParams {
-  const float* bias;
-  const float* R;
-  float* C;
-  int ldr, ldc;
-  int M, N, NT, num_n_tiles, num_chunks, relu;
-  int a_slots, w_slots, w_slot_bytes, acc_sets, tmem_cols, ta_slots;
-  int tiles_per_group, group_mod, group_rows;  // B-matrix selection (0 tiles_per_group = single shared B)
-};
-
-constexpr int kTsThreads = 448;  // producer, MMA, 8 convert warps, 4 epilogue warps
-constexpr int kTsASlotBytes = 128 * 128;
-
-__global__ void __launch_bounds__(kTsThreads, 1)
-gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
-               const __grid_constant__ CUtensorMap tmWl, const TsParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
-  uint8_t* a_ring = smem;
-  uint8_t* w_ring = smem + p.a_slots * kTsASlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + p.w_slots * p.w_slot_bytes);
-  uint64_t* a_full = bars;                 // [8] TMA landed A
-  uint64_t* a_empty = bars + 8;            // [8] convert warps have read the slot (count 4)
-  uint64_t* w_full = bars + 16;            // [8] TMA landed W hi + lo
-  uint64_t* w_empty = bars + 24;           // [8] MMAs that read the slot completed (commit)
-  uint64_t* ta_full = bars + 32;           // [4] (hi, lo) written to the TMEM A slot (count 4)
-  uint64_t* ta_empty = bars + 36;          // [4] MMAs that read the TMEM A slot completed (commit)
-  uint64_t* acc_full = bars + 40;          // [2]
-  uint64_t* acc_empty = bars + 42;         // [2] (count 4)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 512;  // 4 warps x 2 KB
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m_tiles = (p.M + 127) >> 7;
-  const int num_tiles = num_m_tiles * p.num_n_tiles;
-  const int w_half = p.NT * 128;  // bytes of one [NT][32] fp32 tile
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmWh);
-    prefetch_tmap(&tmWl);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
-  }
-  if (threadIdx.x == 64) {
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 8);
-      mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
-    }
-    for (int a = 0; a < 4; ++a) {
-      mbar_init(&ta_full[a], 8);
-      mbar_init(&ta_empty[a], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
-    }
-    fence_mbar_init();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_col0 = p.ta_slots * 64;  // accumulators start after the TMEM A slots
-
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
-        int wrow = nt * p.NT;
-        if (p.tiles_per_group) wrow += ((mt / p.tiles_per_group) % p.group_mod) * p.group_rows;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_arrive_expect_tx(&a_full[sa], kTsASlotBytes);
-          tma_load_2d(a_ring + sa * kTsASlotBytes, &tmA, &a_full[sa], c * 32, mt * 128);
-          mbar_wait(&w_empty[sw], pw ^ 1);
-          mbar_arrive_expect_tx(&w_full[sw], 2 * w_half);
-          tma_load_2d(w_ring + sw * p.w_slot_bytes, &tmWh, &w_full[sw], c * 32, wrow);
-          tma_load_2d(w_ring + sw * p.w_slot_bytes + w_half, &tmWl, &w_full[sw], c * 32, wrow);
-          if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
-          if (++sw == p.w_slots) { sw = 0; pw ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, p.NT);
-      int sw = 0, ta = 0, acc = 0;
-      uint32_t pw = 0, pta = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_main = tmem_base + acc_col0 + acc * 2 * p.NT;
-        const uint32_t d_corr = d_main + p.NT;
-        for (int c = 0; c < p.num_chunks; ++c) {
-          mbar_wait(&ta_full[ta], pta);
-          mbar_wait(&w_full[sw], pw);
-          tc_fence_after();
-          const uint32_t a_hi = tmem_base + ta * 64, a_lo = a_hi + 32;
-          const uint32_t bh = smem_u32(w_ring + sw * p.w_slot_bytes), bl = bh + w_half;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
-            mma_tf32_ts(d_main, a_hi + j * 8, dbh, idesc, (c | j) != 0);
-            mma_tf32_ts(d_corr, a_lo + j * 8, dbh, idesc, (c | j) != 0);
-            mma_tf32_ts(d_corr, a_hi + j * 8, dbl, idesc, 1);
-          }
-          tc_commit(&ta_empty[ta]);
-          tc_commit(&w_empty[sw]);
-          if (++sw == p.w_slots) { sw = 0; pw ^= 1; }
-          if (++ta == p.ta_slots) { ta = 0; pta ^= 1; }
-        }
-        tc_commit(&acc_full[acc]);
-        if (p.acc_sets == 2) {
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-        } else {
-          acc_phase ^= 1;
-        }
-      }
-    }
-  } else if (warp < 10) {
-    // ============================ convert: smem fp32 -> TMEM (hi, lo) =======================
-    // 8 warps: two per TMEM lane quadrant, each converting 16 of the 32 channels of its rows
-    const int q = warp & 3;            // TMEM lane quadrant of this warp
-    const int hh = (warp - 2) >> 2;    // which 16-channel half of the chunk
-    const int row = q * 32 + lane;     // tile row handled by this thread (= TMEM lane)
-    int sa = 0, ta = 0;
-    uint32_t pa = 0, pta = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int c = 0; c < p.num_chunks; ++c) {
-        mbar_wait(&a_full[sa], pa);
-        mbar_wait(&ta_empty[ta], pta ^ 1);
-        tc_fence_after();
-        const float4* arow = reinterpret_cast<const float4*>(a_ring + sa * kTsASlotBytes + row * 128);
-        const uint32_t tdst = tmem_base + ta * 64 + ((uint32_t)(q * 32) << 16);
-        {
-          const int h = hh;  // 16 channels: 4 swizzled 16-byte chunks of the row
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = arow[(h * 4 + j) ^ (row & 7)];
-            float fh, fl;
-            split_tf32(v.x, fh, fl); hi[4 * j] = __float_as_uint(fh); lo[4 * j] = __float_as_uint(fl);
-            split_tf32(v.y, fh, fl); hi[4 * j + 1] = __float_as_uint(fh); lo[4 * j + 1] = __float_as_uint(fl);
-            split_tf32(v.z, fh, fl); hi[4 * j + 2] = __float_as_uint(fh); lo[4 * j + 2] = __float_as_uint(fl);
-            split_tf32(v.w, fh, fl); hi[4 * j + 3] = __float_as_uint(fh); lo[4 * j + 3] = __float_as_uint(fl);
-          }
-          tmem_st_32x16(tdst + h * 16, hi);
-          tmem_st_32x16(tdst + 32 + h * 16, lo);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&a_empty[sa]);  // smem slot can be refilled: nothing else reads A from smem
-          mbar_arrive(&ta_full[ta]);
-        }
-        if (++sa == p.a_slots) { sa = 0; pa ^= 1; }
-        if (++ta == p.ta_slots) { ta = 0; pta ^= 1; }
-      }
-    }
-  } else {
-    // ===================================== epilogue =========================================
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
-      const int n0 = nt * p.NT;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc_col0 + acc * 2 * p.NT + ((uint32_t)(q * 32) << 16);
-      for (int g = 0; g < p.NT; g += 16) {
-        uint32_t r[16], rs[16];
-        tmem_ld_32x16(taddr + g, r);
-        tmem_ld_32x16(taddr + p.NT + g, rs);
-        tmem_ld_wait();
-        if (g + 16 >= p.NT) {  // last group read: hand the accumulators back before the global stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
-              make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(rs[4 * j]),
-                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rs[4 * j + 1]),
-                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rs[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rs[4 * j + 3]));
-        __syncwarp();
-        const int j = lane & 3;
-        const int col = n0 + g + j * 4;
-        if (col < p.N) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll
-          for (int rb = 0; rb < 4; ++rb) {
-            const int rl = rb * 8 + (lane >> 2);
-            const long long grow = (long long)mt * 128 + q * 32 + rl;
-            if (grow < p.M) {
-              float4 o = stg[rl * 4 + (j ^ ((rl >> 1) & 3))];
-              o.x += b.x;
-              o.y += b.y;
-              o.z += b.z;
-              o.w += b.w;
-              if (p.R) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.R + grow * p.ldr + col));
-                o.x += rr.x;
-                o.y += rr.y;
-                o.z += rr.z;
-                o.w += rr.w;
-              }
-              if (p.relu) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = o;
-            }
-          }
-        }
-        __syncwarp();
-      }
-      if (p.acc_sets == 2) {
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      } else {
-        acc_phase ^= 1;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
-  }
-}
-
-// Output-channel tile of the TS kernel: <= 96 keeps two accumulator sets (128 + 4*NT <= 512 columns).
-inline int ts_tile_n(int N) {
-  const int Np = (N + 15) & ~15;
-  if (Np <= 96) return Np;
-  for (int parts = 2; parts <= 16; ++parts)
-    if (Np % parts == 0 && (Np / parts) % 16 == 0 && Np / parts <= 96) return Np / parts;
-  if (Np <= 128) return Np;  // e.g. 112: single accumulator set
-  return 0;
-}
-
-inline int launch_gemm_ts(cudaStream_t s, const float* A, int lda, const float* w_hi, const float* w_lo,
-                          uint64_t w_rows, const float* bias, const float* R, int ldr, float* C, int ldc, int M, int N,
-                          int K, int relu, int tiles_per_group, int group_mod, int group_rows) {
-  if (!g_tc_ready) return -20;
-  TsParams p;
-  p.bias = bias;
-  p.R = R;
-  p.C = C;
-  p.ldr = ldr;
-  p.ldc = ldc;
-  p.M = M;
-  p.N = N;
-  p.NT = ts_tile_n(N);
-  if (!p.NT) return -21;
-  p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
-  p.num_chunks = (K + 31) / 32;
-  p.relu = relu;
-  p.acc_sets = (128 + 4 * p.NT <= 512) ? 2 : 1;
-  p.ta_slots = (256 + p.acc_sets * 2 * p.NT <= 512) ? 4 : 2;
-  if (const char* e = getenv("FEAR_TS_TASLOTS")) p.ta_slots = atoi(e) == 4 && 256 + p.acc_sets * 2 * p.NT <= 512 ? 4 : 2;
-  int cols = 32;
-  while (cols < p.ta_slots * 64 + p.acc_sets * 2 * p.NT) cols <<= 1;
-  p.tmem_cols = cols;
-  p.w_slot_bytes = 2 * p.NT * 128;
-  // A (activations, HBM latency) gets the deep ring; B (weights / templates, mostly L2 hits) needs few slots
-  const int budget = kPwMaxSmem - 1024 - 512 - 8192;
-  p.w_slots = 3;
-  p.a_slots = (budget - p.w_slots * p.w_slot_bytes) / kTsASlotBytes;
-  if (p.a_slots > 8) p.a_slots = 8;
-  if (const char* e = getenv("FEAR_TS_ASLOTS")) p.a_slots = atoi(e);
-  if (p.a_slots < 2) return -22;
-  p.w_slots = (budget - p.a_slots * kTsASlotBytes) / p.w_slot_bytes;
-  if (p.w_slots > 8) p.w_slots = 8;
-  if (p.w_slots < 2) return -22;
-  p.tiles_per_group = tiles_per_group;
-  p.group_mod = group_mod;
-  p.group_rows = group_rows;
-  CUtensorMap tmA, tmWh, tmWl;
-  int r;
-  if (getenv("FEAR_EXP_CONTIG"))  // PERF EXPERIMENT ONLY (wrong results): A boxes contiguous in memory
-    r = make_tmap_2d(&tmA, A, (uint64_t)M * (lda / 32), 32, 32, 128, 32);
-  else
-    r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
-  if (r) return r;
-  r = make_tmap_2d(&tmWh, w_hi, w_rows, (uint64_t)K, (uint64_t)K, p.NT, 32);
-  if (r) return r;
-  r = make_tmap_2d(&tmWl, w_lo, w_rows, (uint64_t)K, (uint64_t)K, p.NT, 32);
-  if (r) return r;
-  const int tiles = ((M + 127) / 128) * p.num_n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  const int smem_bytes = p.a_slots * kTsASlotBytes + p.w_slots * p.w_slot_bytes + 1024 + 512 + 8192;
-  gemm_ts_kernel<<<grid, kTsThreads, smem_bytes, s>>>(tmA, tmWh, tmWl, p);
-  return 0;
-}
-
-// elementwise tf32 split of a device array (template features for the TS correlation)
-__global__ void split_hi_lo_kernel(const float4* __restrict__ src, float4* __restrict__ hi, float4* __restrict__ lo,
-                                   long long n4) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const float4 v = __ldg(src + i);
-  float4 h, l;
-  split_tf32(v.x, h.x, l.x);
-  split_tf32(v.y, h.y, l.y);
-  split_tf32(v.z, h.z, l.z);
-  split_tf32(v.w, h.w, l.w);
-  hi[i] = h;
-  lo[i] = l;
-}
-
-  // 227 KB opt-in limit minus static/driver slack
-
 // Output-channel tile for a layer: largest divisor-style tile <= 256 that is a multiple of 16.
 // wide = single-chunk layers (K <= 32, one accumulator per stage): tiles up to 256 columns.  Those layers are
 // bound by the per-tile round trips (TMA -> split -> MMA -> epilogue), so fewer, wider tiles win.
@@ -1360,33 +769,14 @@ inline int pw_tile_n(int N, bool wide = false) {
   return 0;
 }
 
-// z_hi / z_lo: tf32 split planes of zt (split_hi_lo_kernel), [Bz*64][256] each.
-inline int launch_corr2(cudaStream_t s, const float* z_hi, const float* z_lo, int Bz, float* cat, int B, int groups) {
-  if (!g_tc_ready) return -20;
-  CUtensorMap tmA, tmBh, tmBl;
-  const int frames = B * groups;
-  int r = make_tmap_2d(&tmA, cat, (uint64_t)frames * 256, 320, 320, 128, kCorrChunk);
-  if (r) return r;
-  r = make_tmap_2d(&tmBh, z_hi, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
-  if (r) return r;
-  r = make_tmap_2d(&tmBl, z_lo, (uint64_t)Bz * 64, 256, 256, 64, kCorrChunk);
-  if (r) return r;
-  const int tiles = frames * 2;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  corr_tc2_kernel<<<grid, kC2Threads, kC2SmemBytes, s>>>(tmA, tmBh, tmBl, cat, frames, Bz == 1 ? 0 : B);
-  return 0;
-}
-
 inline bool pw_supported(int cin, int cout) {
-  return g_tc_ready && cin % 8 == 0 && cout % 8 == 0 && pw_tile_n(cout) != 0;
+  return available() && cin % 8 == 0 && cout % 8 == 0 && pw_tile_n(cout) != 0;
 }
 
 inline int init_pw() {
-  if (cudaFuncSetAttribute(corr_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes) != cudaSuccess ||
-      cudaFuncSetAttribute(pw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+  if (cudaFuncSetAttribute(pw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(pw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
+      cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
@@ -1396,7 +786,7 @@ inline int init_pw() {
 // w_hi / w_lo: tf32-split copies of the [N][K] weights (device).
 inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi, const float* w_lo, const float* bias,
                      const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu) {
-  if (!g_tc_ready) return -20;
+  if (!available()) return -20;
   PwParams p;
   p.bias = bias;
   p.R = R;
@@ -1406,7 +796,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.M = M;
   p.N = N;
   p.num_chunks = (K + 31) / 32;
-  p.NT = pw_tile_n(N, p.num_chunks == 1 && !getenv("FEAR_PW_NARROW"));
+  p.NT = pw_tile_n(N, p.num_chunks == 1);
   if (!p.NT) return -21;
   p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
   p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
@@ -1414,7 +804,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
   p.dw_relu = p.dw_bias = p.box_bytes = 0;
-  const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1 && !getenv("FEAR_PW_NO_RESIDENT");
+  const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1;
   p.w_region = resident ? 2 * p.NT * 128 : 0;
   p.stage_bytes = resident ? 2 * kCorrABytes : 2 * kCorrABytes + 2 * p.NT * 128;
   p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region) / p.stage_bytes;
@@ -1431,7 +821,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   r = make_tmap_2d(&tmWl, w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
   if (r) return r;
   const int tiles = ((M + 127) / 128) * p.num_n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   CUtensorMap tmC;  // output: [M][N] window of C (pitch ldc); 32 x 16 boxes, SWIZZLE_64B staging; clips the tails
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
@@ -1448,7 +838,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
 inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const float* dw_w, const float* dw_b, int dw_relu,
                         const float* w_hi, const float* w_lo, const float* bias, const float* R, int ldr, float* C,
                         int ldc, int N, int K, int relu) {
-  if (!g_tc_ready) return -20;
+  if (!available()) return -20;
   if ((dw_k != 3 && dw_k != 5) || K % 4) return 1;
   PwParams p;
   const int M = B * 256;
@@ -1496,7 +886,7 @@ inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const f
     tmDB = tmDW;
   }
   const int tiles = (M / 128) * p.num_n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   const size_t smem_bytes = (size_t)2 * p.stage_bytes + 1024 + kPwTailBytes;
   cudaError_t e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC,
                                          tmDW, tmDB, p)

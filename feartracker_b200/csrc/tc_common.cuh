@@ -10,6 +10,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <mutex>
+#include <set>
+#include <string>
+#include <unordered_map>
+
 namespace fear {
 namespace tc {
 
@@ -35,22 +40,90 @@ inline int resolve_driver() {
   return 0;
 }
 
+// ---- per-device library state -----------------------------------------------------------------
+// cudaFuncSetAttribute and the "is this an sm_100 with a working driver entry point" answer are PER DEVICE, so they
+// are keyed by the current device (every C entry point selects its handle's device before launching anything).
+struct DeviceState {
+  bool inited = false;    // fear_init() ran for this device
+  bool tc_ready = false;  // tensor-core / TMA path usable
+  int num_sms = 0;
+  std::set<const void*> attrs;  // kernels whose opt-in shared-memory attribute has been set on this device
+};
+inline std::mutex& state_mutex() {
+  static std::mutex m;
+  return m;
+}
+inline DeviceState& dev_state() {
+  static DeviceState st[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  return st[d & 63];
+}
+inline bool available() { return dev_state().tc_ready; }
+inline int num_sms() { return dev_state().num_sms; }
+// true exactly once per (device, kernel): the caller then sets the kernel's attributes.
+inline bool attr_needed(const void* fn) {
+  std::lock_guard<std::mutex> lock(state_mutex());
+  return dev_state().attrs.insert(fn).second;
+}
+
+// ---- tensor maps (cached) ------------------------------------------------------------------------
+// Encoding a CUtensorMap is a pure host-side function of (base, dims, strides, box, swizzle); the executor asks
+// for the same few hundred maps every step (workspace pointers are stable), so they are memoised per host thread.
+struct TmapKey {
+  uint64_t v[16];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 1099511628211ull;
+    }
+    return (size_t)h;
+  }
+};
+inline int encode_cached(CUtensorMap* m, CUtensorMapDataType dt, uint32_t rank, const void* base, const cuuint64_t* dims,
+                         const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle sw,
+                         CUtensorMapL2promotion promo) {
+  if (resolve_driver()) return -10;
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.v[0] = (uint64_t)(uintptr_t)base;
+  k.v[1] = ((uint64_t)dt << 32) | ((uint64_t)rank << 16) | ((uint64_t)sw << 8) | (uint64_t)promo;
+  for (uint32_t i = 0; i < rank; ++i) {
+    k.v[2 + i] = dims[i];
+    k.v[7 + i] = (i + 1 < rank) ? strides[i] : 0;
+    k.v[12 + (i >> 1)] |= (uint64_t)box[i] << (32 * (i & 1));
+  }
+  auto it = cache.find(k);
+  if (it != cache.end()) {
+    *m = it->second;
+    return 0;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(m, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -11;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(k, *m);
+  return 0;
+}
+
 // 2-D fp32 row-major tensor [rows][cols] with row pitch `pitch_floats`; box = [box_rows][box_cols];
 // 128-byte swizzle when box_cols * 4 == 128, 64-byte swizzle for 64-byte rows, none otherwise.
 inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_floats,
                         uint32_t box_rows, uint32_t box_cols) {
-  if (resolve_driver()) return -10;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
   cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = (box_cols * 4 == 128)  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : (box_cols * 4 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
+  return encode_cached(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 // 4-D fp32 channels-last activation tensor [B][H][W][C] (dims listed innermost first: C, W, H, B), no swizzle.
@@ -58,44 +131,31 @@ inline int make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
 // exactly the zero padding of a "same" convolution (and it still counts the full box bytes on the mbarrier).
 inline int make_tmap_nhwc(CUtensorMap* m, const float* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                           uint32_t box_c, uint32_t box_w, uint32_t box_h) {
-  if (resolve_driver()) return -10;
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
+  return encode_cached(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 // Generic unswizzled 3-D map (dims / box innermost first, strides in bytes for dims 1 and 2); out-of-range
 // elements read as zero.  Used for the image patches of the fused stem kernel (fp32 planes or uint8 HWC rows).
 inline int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                         uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
-  if (resolve_driver()) return -10;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {b0, b1, b2};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode_fn()(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
+  return encode_cached(m, dt, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 // Plain (unswizzled) 2-D map, used for the small per-layer weight / bias tables.
 inline int make_tmap_2d_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                               uint32_t box_cols) {
-  if (resolve_driver()) return -10;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * sizeof(float)};
   cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
+  return encode_cached(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
 // Launch `kern` with programmatic stream serialization (PDL) unless disabled or the stream is being captured

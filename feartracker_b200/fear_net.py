@@ -5,9 +5,11 @@ constructor keywords (extras swallowed by ``**kwargs`` because hydra passes ever
 same sub-module / parameter names so ``load_state_dict(strict=True)`` of the shipped Lightning
 checkpoint works, same methods and output dictionary.  The nn.Module tree below only HOLDS
 parameters; arithmetic never runs in PyTorch.  On first use in eval mode the parameters are
-BN-folded (float64) and packed into the library; ``load_state_dict`` / ``train`` / ``.to`` /
-``.cuda`` invalidate the packed copy.  No CPU path and no training path: non-CUDA inputs or
-``train()`` mode raise.
+BN-folded (float64) and packed into the library; ``load_state_dict`` / ``train()`` / ``.to`` /
+``.cuda`` invalidate the packed copy.  Eval mode has no CPU path (non-CUDA inputs raise).  In ``train()`` mode
+(BatchNorm batch statistics + autograd, which the inference kernels do not provide) the same methods run the plain
+PyTorch graph of ``torch_graph.py`` over the same parameters -- NOT accelerated; it exists so the reference's training
+step (``FEARLightningModel.forward`` -> ``model.forward``, fear_lightning_model.py:60-62) runs on this class.
 """
 import ctypes
 import weakref
@@ -18,7 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, weights
+from . import _lib, torch_graph, weights
 from .constants import TARGET_CLASSIFICATION_KEY, TARGET_REGRESSION_LABEL_KEY
 
 # (name, cin, cout, kernel, stride, expansion) of fbnet_c's 24 stages; expansion None = plain
@@ -129,10 +131,9 @@ class BoxTower(_Params):
         owner = self._owner() if self._owner is not None else None
         if owner is None:
             return super().forward()
-        if update is not None:
-            raise NotImplementedError("the dynamic-template `update` input is not wired in the B200 head yet "
-                                      "(never passed by the reference either, fear_net.py:77)")
-        out = owner.connector(kernel, search)
+        if owner.training:
+            return torch_graph.box_tower(owner, search, kernel, update)
+        out = owner._head(kernel, search, update)  # update: dynamic template of the cls branch (blocks.py:174-179)
         b = search.shape[0]
         return (out[TARGET_REGRESSION_LABEL_KEY], out[TARGET_CLASSIFICATION_KEY],
                 owner.head_tensor("cls_dw", b), owner.head_tensor("x_reg", b))
@@ -213,6 +214,8 @@ class FEARNet(nn.Module):
 
     def feature_extractor(self, x: torch.Tensor) -> torch.Tensor:
         """(B,3,H,W) -> (B,112,H/16,W/16): fbnet_c stages 0..17."""
+        if self.training:
+            return torch_graph.feature_extractor(self, x)
         x, h, lib = self._prep(x)
         b, _, hh, ww = x.shape
         out = torch.empty((b, 112, hh // 16, ww // 16), device=x.device, dtype=torch.float32)
@@ -222,6 +225,8 @@ class FEARNet(nn.Module):
     def get_features(self, crop: torch.Tensor) -> torch.Tensor:
         """(B,3,H,W) float -> (B,256,H/16,W/16).  A uint8 (B,H,W,3) RGB crop is also accepted: it is
         ImageNet-normalised inside the stem kernel (bit-identical to Tracker._preprocess_image on the host)."""
+        if self.training:
+            return torch_graph.get_features(self, crop)
         if crop.dtype == torch.uint8:
             x, h, lib = self._prep(crop, keep_dtype=True)
             b, hh, ww, ch = x.shape
@@ -239,19 +244,34 @@ class FEARNet(nn.Module):
         return out
 
     def connector(self, template_features: torch.Tensor, search_features: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if self.training:
+            return torch_graph.connector(self, template_features, search_features)
+        return self._head(template_features, search_features, None)
+
+    def _head(self, template_features: torch.Tensor, search_features: torch.Tensor,
+              update: Optional[torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """BoxTower.forward(search, kernel, update) in the library (fear_head_update); update = None is the
+        reference's only call pattern (fear_net.py:77)."""
         xf, h, lib = self._prep(search_features)
         zf = self._as_input(template_features, xf.device)
         b = xf.shape[0]
         self._check_shapes(zf, b)
+        zu = None
+        if update is not None:
+            zu = self._as_input(update, xf.device)
+            self._check_shapes(zu, b)
         if tuple(xf.shape[1:]) != (256, 16, 16):
             raise ValueError(f"search features must be (B,256,16,16), got {tuple(xf.shape)}")
         bbox = torch.empty((b, 4, 16, 16), device=xf.device, dtype=torch.float32)
         cls = torch.empty((b, 1, 16, 16), device=xf.device, dtype=torch.float32)
-        _lib.check(lib.fear_head(h, zf.data_ptr(), zf.shape[0], xf.data_ptr(), b, bbox.data_ptr(), cls.data_ptr(),
-                                 self._stream(xf)), "fear_head")
+        _lib.check(lib.fear_head_update(h, zf.data_ptr(), zf.shape[0], zu.data_ptr() if zu is not None else None,
+                                        zu.shape[0] if zu is not None else 0, xf.data_ptr(), b, bbox.data_ptr(),
+                                        cls.data_ptr(), self._stream(xf)), "fear_head_update")
         return {TARGET_REGRESSION_LABEL_KEY: bbox, TARGET_CLASSIFICATION_KEY: cls}
 
     def forward(self, x: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self.training:
+            return torch_graph.forward(self, x)
         template, search = x
         s, h, lib = self._prep(search)
         t = self._as_input(template, s.device)
@@ -267,6 +287,8 @@ class FEARNet(nn.Module):
         return {TARGET_REGRESSION_LABEL_KEY: bbox, TARGET_CLASSIFICATION_KEY: cls}
 
     def track(self, search: torch.Tensor, template_features: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if self.training:
+            return torch_graph.track(self, search, template_features)
         out, _ = self._track(search, template_features, want_maps=True, want_boxes=False)
         return out
 
@@ -375,6 +397,13 @@ class FEARNet(nn.Module):
         h, lib = self._ensure_handle(dev)
         _lib.check(lib.fear_set_option(h, key.encode(), value.encode()), "fear_set_option")
 
+    def generation(self):
+        """Changes whenever CUDA-graph captures of calls on this net go stale: weights re-packed (new handle),
+        workspace re-allocated by a larger ``reserve`` / batch, or an option changed."""
+        if self._handle is None:
+            return None
+        return (self._handle.value, int(_lib.load().fear_generation(self._handle)))
+
     def launch_count(self) -> int:
         return int(_lib.load().fear_launch_count(self._handle)) if self._handle is not None else 0
 
@@ -433,9 +462,7 @@ class FEARNet(nn.Module):
 
     def _prep(self, x: torch.Tensor, keep_dtype: bool = False):
         if self.training:
-            raise NotImplementedError(
-                "FEARNet (B200) runs inference only: call .eval().  The training step (BN batch statistics, "
-                "autograd) is outside the accelerated hot path (SURVEY.md section 8(f)-3)")
+            raise RuntimeError("internal: the library path was entered in train() mode")
         if not x.is_cuda:
             raise RuntimeError("FEARNet (B200) has no CPU path: inputs must be CUDA tensors on a B200 (sm_100)")
         x = x.detach().contiguous() if keep_dtype else self._as_input(x, x.device)
@@ -451,18 +478,19 @@ class FEARNet(nn.Module):
         if self._handle is not None and self._handle_device == index:
             return self._handle, _lib.load()
         self._drop_handle()
-        lib = _lib.init(index)
         sd = {k: v for k, v in self.state_dict().items() if v.is_floating_point()}
-        blob, offsets = weights.pack(sd, _lib.weight_table())
-        handle = ctypes.c_void_p()
-        _lib.check(
-            lib.fear_pack_weights(blob.ctypes.data_as(ctypes.c_void_p),
-                                  offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(offsets) - 1,
-                                  ctypes.byref(handle)),
-            "fear_pack_weights")
-        self._handle, self._handle_device = handle, index
-        if self._reserved > 1:
-            _lib.check(lib.fear_reserve(handle, self._reserved), "fear_reserve")
+        with torch.cuda.device(index):  # the handle belongs to the device current at pack time; caller's is restored
+            lib = _lib.init(index)
+            blob, offsets = weights.pack(sd, _lib.weight_table())
+            handle = ctypes.c_void_p()
+            _lib.check(
+                lib.fear_pack_weights(blob.ctypes.data_as(ctypes.c_void_p),
+                                      offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(offsets) - 1,
+                                      ctypes.byref(handle)),
+                "fear_pack_weights")
+            self._handle, self._handle_device = handle, index
+            if self._reserved > 1:
+                _lib.check(lib.fear_reserve(handle, self._reserved), "fear_reserve")
         return handle, lib
 
     def _drop_handle(self) -> None:
@@ -475,7 +503,10 @@ class FEARNet(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def train(self, mode: bool = True):
-        self._drop_handle()
+        # the packed copy only goes stale when parameters can change, i.e. on entering train(); eval() -> eval()
+        # (a common per-sequence idiom) keeps the handle, its workspace and any captured CUDA graph
+        if mode:
+            self._drop_handle()
         return super().train(mode)
 
     def _apply(self, fn, *args, **kwargs):

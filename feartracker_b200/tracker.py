@@ -60,7 +60,12 @@ class Tracker:
     def _device(self) -> torch.device:
         if not torch.cuda.is_available():
             raise RuntimeError("FEARTracker (B200) needs a CUDA device: there is no CPU path")
-        return torch.device("cuda", self.cuda_id if isinstance(self.cuda_id, int) else 0)
+        if isinstance(self.cuda_id, int):
+            return torch.device("cuda", self.cuda_id)
+        dev = torch.device(self.cuda_id)  # the reference also takes device strings ("cuda:1")
+        if dev.type != "cuda":
+            raise RuntimeError(f"FEARTracker (B200) needs a CUDA device, got {self.cuda_id!r}: there is no CPU path")
+        return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
 
     def _preprocess_image(self, image: np.ndarray, transform=None) -> torch.Tensor:
         """uint8 HWC crop -> network input on the tracker's device.
@@ -108,6 +113,8 @@ class FEARTracker(Tracker):
 
     def update(self, image: np.ndarray, *kw) -> Dict[str, Any]:
         st, cfg = self.tracking_state, self.tracking_config
+        if cfg.get("gpu_crop", False):
+            return self._update_gpu_crop(image)
         crop, search_bbox, context = image_ops.extended_crop(image, st.bbox, cfg["instance_size"],
                                                              cfg["search_context"], st.mean_color)
         st.mapping = context
@@ -117,6 +124,9 @@ class FEARTracker(Tracker):
         st.bbox = pred_bbox
         st.paths.append(pred_bbox)
         return dict(bbox=pred_bbox)
+
+    def _update_gpu_crop(self, image: np.ndarray) -> Dict[str, Any]:
+        raise NotImplementedError("gpu_crop: on-device crop + resize is not built in this library version")
 
     def track(self, search_crop: np.ndarray) -> Tuple[np.ndarray, float]:
         if self.tracking_config.get("smooth", False):
@@ -141,7 +151,7 @@ class FEARTracker(Tracker):
                       dev=torch.empty(shape, dtype=dtype, device=dev),
                       zf=torch.empty((1, 256, 8, 8), dtype=torch.float32, device=dev),
                       box_pin=torch.empty((1, 48), dtype=torch.uint8).pin_memory(),
-                      graph=None, boxes=None, handle=None, zf_src=None, calls=0)
+                      graph=None, boxes=None, generation=None, zf_src=None, calls=0, graph_ok=True)
             self._stream_state = st
         if host_norm:
             np.copyto(st["pin"].numpy(), np.transpose(image_ops.normalize(search_crop[:, :, :3]), (2, 0, 1))[None])
@@ -151,20 +161,25 @@ class FEARTracker(Tracker):
         if st["zf_src"] is not self._template_features:  # new template (initialize / reset): refresh the static copy
             st["zf"].copy_(self._template_features)
             st["zf_src"] = self._template_features
-        use_graph = self.tracking_config.get("cuda_graph", True)
-        handle = getattr(self.net, "_handle", None)
-        if use_graph and st["graph"] is not None and st["handle"] is not handle:
-            st["graph"], st["calls"] = None, 0  # weights were re-packed: the captured pointers are stale
+        use_graph = self.tracking_config.get("cuda_graph", True) and st["graph_ok"]
+        if st["graph"] is not None and st["generation"] != self.net.generation():
+            # weights re-packed, workspace re-allocated by a larger batch on the same net, or an option changed:
+            # the pointers / kernels baked into the captured graph are stale -> warm up eagerly and capture again
+            st["graph"], st["calls"] = None, 0
         if use_graph and st["graph"] is None and st["calls"] >= 1:
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     st["boxes"] = self.net.track_boxes(st["dev"], st["zf"])
-                st["graph"], st["handle"] = g, getattr(self.net, "_handle", None)
-            except Exception:  # capture unsupported in this context: stay eager
-                self.tracking_config["cuda_graph"] = False
+                st["graph"], st["generation"] = g, self.net.generation()
+            except RuntimeError as exc:  # capture failed: stay eager for this tracker, loudly
+                import warnings
+
+                warnings.warn(f"FEARTracker: CUDA-graph capture of the per-frame step failed ({exc}); "
+                              "falling back to eager launches (slower streaming path)")
+                st["graph_ok"] = False
                 torch.cuda.synchronize(dev)
-        if use_graph and st["graph"] is not None and self.tracking_config.get("cuda_graph", True):
+        if use_graph and st["graph"] is not None and st["graph_ok"]:
             st["graph"].replay()
             boxes = st["boxes"]
         else:
@@ -208,7 +223,9 @@ class FEARTracker(Tracker):
         flat = int(np.argmax(pscore))
         r, c = flat // 16, flat % 16
         box = np.array([x1[r, c], y1[r, c], x2[r, c] - x1[r, c], y2[r, c] - y1[r, c]])
-        lr = float(penalty[r, c] * score[r, c] * cfg["lr"])
+        # the reference multiplies a float64 numpy scalar into a float32 torch scalar (base_tracker.py:158): the size
+        # learning rate is therefore rounded to float32 at each step -- reproduced here so boxes match to the last bit
+        lr = (float(penalty[r, c]) * torch.tensor(score[r, c], dtype=torch.float32) * cfg["lr"]).item()
         size, prev = box[2:] * lr, np.asarray(st.prev_size) * (1 - lr)
         w = prev[0] + lr * (size[0] + prev[0])
         h = prev[1] + lr * (size[1] + prev[1])

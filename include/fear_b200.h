@@ -16,17 +16,23 @@
  *   fear_decode           FEARBoxCoder.decode                 dataset/box_coder.py:75-107
  *   fear_pack_weights     load_from_lighting + nn.Module.load_state_dict  utils/torch.py:11-24
  *
+ *   fear_head_update      BoxTower.forward(search, kernel, update)   blocks.py:174-179
+ *
  * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (torch keeps
  * ownership); tensors are dense fp32 in the reference's NCHW layout unless stated; `stream`
- * is a cudaStream_t passed as void*.  Calls are asynchronous on `stream`, never synchronise
- * it and never allocate (workspace is reserved up front by fear_reserve; a batch larger than
- * the reservation is processed in chunks).  Return 0 on success, a positive cudaError_t or a
- * negative FEAR_E* code otherwise; fear_last_error() gives the message (thread-local).
- * Handles are not thread-safe: one handle per host thread / stream.
+ * is a cudaStream_t passed as void*.  Hot-path calls are asynchronous on `stream`, never synchronise
+ * it and never allocate (workspace is reserved up front by fear_reserve -- the only call besides
+ * fear_pack_weights / fear_free that allocates or synchronises; a batch larger than the reservation is
+ * processed in chunks; fear_corr_concat_ws_f32 takes its scratch from the caller).  Return 0 on success,
+ * a positive cudaError_t or a negative FEAR_E* code otherwise; fear_last_error() gives the message
+ * (thread-local).  Handles are not thread-safe: one handle per host thread / stream.  A handle belongs to the
+ * device that was current when it was packed; every entry point selects that device for its own duration and
+ * restores the caller's current device (several devices per process are fine: call fear_init for each).
  */
 #ifndef FEAR_B200_H
 #define FEAR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -56,7 +62,8 @@ typedef struct FearBox {
 
 typedef struct FearContext FearContext;
 
-/* Select the device and verify it is sm_100.  Call once per process before anything else. */
+/* Verify `device` is sm_100, initialise the library's per-device state and make it the current device
+ * (like torch's .cuda(id)).  Call once per device before packing weights on it; repeated calls are cheap. */
 int fear_init(int device);
 int fear_abi_version(void);
 const char* fear_last_error(void);
@@ -89,6 +96,12 @@ int fear_backbone(FearContext* h, const float* d_img, int B, int H, int W, float
 int fear_head(FearContext* h, const float* d_zfeat, int Bz, const float* d_xfeat, int B,
               float* d_bbox, float* d_cls, void* stream);
 
+/* BoxTower.forward(search, kernel, update) (blocks.py:174-179): as fear_head, but the CLASSIFICATION branch correlates
+ * with the dynamic template d_zupdate (Bu,256,8,8), Bu == B or 1, while the regression branch keeps d_zfeat.
+ * d_zupdate == NULL is exactly fear_head. */
+int fear_head_update(FearContext* h, const float* d_zfeat, int Bz, const float* d_zupdate, int Bu, const float* d_xfeat,
+                     int B, float* d_bbox, float* d_cls, void* stream);
+
 /* search (B,3,256,256) + zfeat (Bz,256,8,8) -> maps and (if non-null) decoded boxes[B].
  * d_bbox / d_cls may be null when only boxes are wanted. */
 int fear_track(FearContext* h, const float* d_search, const float* d_zfeat, int Bz, int B,
@@ -112,8 +125,14 @@ int fear_decode(const float* d_bbox, const float* d_cls, int B, int apply_sigmoi
                 void* stream);
 
 /* z (Bz,256,64), x (B,256,256)  [= (B,256,16,16)]  ->  out (B,320,256):
- * out[:, :256] = x ; out[b, 256+k, p] = sum_c z[b,c,k] * x[b,c,p].   (blocks.py:121-124) */
+ * out[:, :256] = x ; out[b, 256+k, p] = sum_c z[b,c,k] * x[b,c,p].   (blocks.py:121-124)
+ * Workspace-free compatibility form: a direct CUDA-core kernel on the reference layouts (one D2D copy + one launch). */
 int fear_corr_concat_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* stream);
+/* Same result through the hot path's tcgen05 kernel (layout changes in the caller's scratch: d_workspace must be
+ * 1024-byte aligned and hold fear_corr_concat_workspace_bytes(B, Bz) bytes). */
+size_t fear_corr_concat_workspace_bytes(int B, int Bz);
+int fear_corr_concat_ws_f32(const float* d_z, int Bz, const float* d_x, int B, float* d_out, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* Channels-last core of the same contraction (the kernel the hot path launches):
  * zt (Bz,64,256) [k][c], cat (B,256,320) [p][c'] whose first 256 channels hold x;
@@ -123,16 +142,20 @@ int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* str
 /* ---- introspection (tests / bench) ---------------------------------------------------*/
 /* Select a kernel implementation for a stage by name.  Returns FEAR_EINVAL for unknown names.
  * Default = best validated implementation; every alternative is parity-tested against it.
- *   "corr", "pw"   : "auto" | "ffma" | "tcgen05" | "tcgen05ts" | "tcgen05v2"   (correlation / 1x1 convs)
- *   "dw"           : "auto" | "pixel" | "strip" | "roll" | "tile" | "blocked" | "tma"   (depthwise)
+ *   "corr", "pw"   : "auto" | "ffma" | "tcgen05"                  (correlation / 1x1 convs; ffma = CUDA-core baseline)
+ *   "dw"           : "auto" | "pixel" | "strip" | "roll" | "tma"  (depthwise)
  *   "fuse_stem"    : "1" (default) stem + xif1_0 in one kernel | "0" four separate kernels
- *   "small_const"  : "1" (default) tiny 1x1 convs take their weights by value (constant bank) | "0" via smem
- *   "fuse_dwpw"    : EXPERIMENTAL bit mask (default 0): 1 = 16x16-stage blocks, 2 = head SepConvs run their depthwise conv
- *                    inside the 1x1 GEMM kernel; "pdl": "1" (default) programmatic dependent launch
- *   "fuse", "early_sub", "dw_wide" : measured-slower experiments, off by default */
+ *   "fuse_irf"     : "1" (default) xif2_0 (expand 1x1 -> depthwise 3x3 s2 -> project 1x1) in ONE tcgen05 kernel, the
+ *                    6x expanded tensor never leaves the SM | "0" three kernels
+ *   "fuse_dwpw"    : bit mask (default 0): 1 = 16x16-stage blocks, 2 = head SepConvs run their depthwise conv inside
+ *                    the 1x1 GEMM kernel (bit-identical, perf-neutral)
+ *   "pdl"          : "1" (default) programmatic dependent launch (process-wide) */
 int fear_set_option(FearContext* h, const char* key, const char* value);
 /* Number of kernels launched by this handle since creation (for bench's gpu_launches). */
 int64_t fear_launch_count(const FearContext* h);
+/* Changes whenever the handle's workspace pointers or options change (fear_reserve growth, fear_set_option):
+ * a CUDA graph captured from calls on this handle is stale once the value differs from the one seen at capture. */
+int64_t fear_generation(const FearContext* h);
 /* When enabled, every stage of the next calls is bracketed by CUDA events on `stream`;
  * fear_stage_ms returns accumulated milliseconds and launch counts (synchronises events). */
 int fear_profile(FearContext* h, int enable);

@@ -304,9 +304,60 @@ def rescale_bbox(bbox: np.ndarray, padded_box, instance_size: int = 256) -> List
     return list(map(int, bbox))
 
 
+def limit(radius):
+    """utils/utils.py:74-77."""
+    if isinstance(radius, torch.Tensor):
+        return torch.maximum(radius, 1.0 / radius)
+    return np.maximum(radius, 1.0 / radius)
+
+
+def squared_size(w, h):
+    """utils/utils.py:80-85."""
+    pad = (w + h) * 0.5
+    size = (w + pad) * (h + pad)
+    if isinstance(size, torch.Tensor):
+        return torch.sqrt(size)
+    return np.sqrt(size)
+
+
+def tracking_window(windowing: str, score_size: int) -> torch.Tensor:
+    """base_tracker.py:57-67."""
+    if windowing == "cosine":
+        return torch.from_numpy(np.outer(np.hanning(score_size), np.hanning(score_size)))
+    return torch.ones(int(score_size), int(score_size))
+
+
+def confidence_postprocess(cls_score: torch.Tensor, regression_map: torch.Tensor, prev_size, window: torch.Tensor,
+                           config: dict):
+    """base_tracker.py:166-205 with ``smooth: true``: scale / ratio penalty and cosine-window re-weighting of the
+    score map.  cls_score (1,1,16,16) float32 (sigmoid applied), regression_map (1,4,16,16) -> (pscore, penalty)."""
+    grid_x, grid_y = make_grid(config["score_size"], config["total_stride"], config["instance_size"])
+    pred_location = torch.stack(
+        [grid_x - regression_map[:, 0, ...], grid_y - regression_map[:, 1, ...],
+         grid_x + regression_map[:, 2, ...], grid_y + regression_map[:, 3, ...]], dim=1)[0]
+    s_c = limit(squared_size(pred_location[2] - pred_location[0], pred_location[3] - pred_location[1])
+                / (squared_size(prev_size[0], prev_size[1])))
+    r_c = limit((prev_size[0] / prev_size[1])
+                / ((pred_location[2] - pred_location[0]) / (pred_location[3] - pred_location[1])))
+    penalty = torch.exp(-(r_c * s_c - 1) * config["penalty_k"])
+    pscore = penalty * cls_score
+    pscore = pscore * (1 - config["window_influence"]) + window * config["window_influence"]
+    return pscore, penalty.cpu().numpy()
+
+
+def smooth_size(size: np.ndarray, prev_size: np.ndarray, lr: float):
+    """base_tracker.py:126-139."""
+    size = size * lr
+    prev_size = prev_size * (1 - lr)
+    w = prev_size[0] + lr * (size[0] + prev_size[0])
+    h = prev_size[1] + lr * (size[1] + prev_size[1])
+    return w, h
+
+
 class OracleTracker:
-    """fear_tracker.py:13-86 + base_tracker.py:28-124 with the default config (no ``smooth`` key,
-    so _confidence_postprocess / _postprocess_bbox are pass-throughs, base_tracker.py:152,174)."""
+    """fear_tracker.py:13-86 + base_tracker.py:28-205.  With the default config (no ``smooth`` key)
+    _confidence_postprocess / _postprocess_bbox are pass-throughs (base_tracker.py:152,174); ``smooth=True`` in the
+    config enables the penalty / window / size-smoothing branch."""
 
     def __init__(self, sd: StateDict, config: dict = TRACKER_CONFIG):
         self.sd, self.cfg = sd, dict(config)
@@ -315,8 +366,10 @@ class OracleTracker:
         self.mean_color = None
         self.template_features = None
         self.paths = None
+        self.prev_size = None
         self.last_search_crop = None
         self.last_maps = None
+        self.window = tracking_window(self.cfg["windowing"], self.cfg["score_size"])
 
     def initialize(self, image: np.ndarray, rect) -> None:
         rect = clamp_bbox(rect, image.shape)
@@ -328,18 +381,35 @@ class OracleTracker:
         with torch.no_grad():
             self.template_features = get_features(self.sd, preprocess_image(crop).to(self.dtype))
 
+    def postprocess(self, out):
+        """FEARTracker._postprocess (fear_tracker.py:74-86) on a maps dictionary."""
+        cls_score = out[TARGET_CLASSIFICATION_KEY].detach().float().sigmoid()
+        regression_map = out[TARGET_REGRESSION_LABEL_KEY].detach().float()
+        penalty = None
+        classification_map = cls_score
+        if self.cfg.get("smooth", False):
+            classification_map, penalty = confidence_postprocess(cls_score, regression_map, self.prev_size, self.window,
+                                                                 self.cfg)
+        bbox, coords = decode(out[TARGET_REGRESSION_LABEL_KEY], classification_map, use_sigmoid=False, config=self.cfg)
+        r, c = coords[0]
+        cls_np = np.squeeze(cls_score)
+        pred_bbox = np.squeeze(bbox.cpu().numpy())
+        if self.cfg.get("smooth", False):  # _postprocess_bbox, base_tracker.py:147-164
+            lr = (penalty[r, c] * cls_np[r, c] * self.cfg["lr"]).item()
+            pred_w, pred_h = smooth_size(np.array(pred_bbox[2:]), prev_size=self.prev_size, lr=lr)
+            pred_bbox = np.array([pred_bbox[0], pred_bbox[1], pred_w, pred_h])
+        return pred_bbox, cls_np[r, c], (r, c)
+
     def track(self, search_crop: np.ndarray):
         out = track(self.sd, preprocess_image(search_crop).to(self.dtype), self.template_features)
         self.last_maps = out
-        cls_score = out[TARGET_CLASSIFICATION_KEY].detach().float().sigmoid()
-        bbox, coords = decode(out[TARGET_REGRESSION_LABEL_KEY], cls_score, use_sigmoid=False, config=self.cfg)
-        r, c = coords[0]
-        return np.squeeze(bbox.cpu().numpy()), np.squeeze(cls_score)[r, c], (r, c)
+        return self.postprocess(out)
 
     def update(self, image: np.ndarray) -> Dict[str, np.ndarray]:
         crop, search_bbox, padded = get_extended_crop(
             image, self.bbox, self.cfg["instance_size"], self.cfg["search_context"], self.mean_color)
         self.last_search_crop = crop
+        self.prev_size = search_bbox[2:]
         pred, _, _ = self.track(crop)
         pred = rescale_bbox(pred, padded, self.cfg["instance_size"])
         pred = clamp_bbox(pred, image.shape)

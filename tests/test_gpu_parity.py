@@ -229,7 +229,7 @@ def test_free_running_video_trajectory(net):
     assert ious.min() > 0.8 and ious.mean() > 0.98, (float(ious.min()), float(ious.mean()), first_diff)
 
 
-@pytest.mark.parametrize("impl", ["strip", "roll", "tile", "blocked", "tma"])
+@pytest.mark.parametrize("impl", ["strip", "roll", "tma"])
 def test_depthwise_variants_are_bit_identical(net, impl):
     """The register-strip / rolling-window depthwise kernels accumulate in the same order as the per-pixel one."""
     zt, xt, _, _ = fo.synthetic_crops(2)
@@ -244,37 +244,6 @@ def test_depthwise_variants_are_bit_identical(net, impl):
         net.set_option("dw", "auto")
     assert torch.equal(zf, zf2)
     assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
-
-
-def test_l2_sub_batching_is_bit_identical(net):
-    """Running the high-resolution blocks in sub-batches (L2 blocking) must not change a single bit."""
-    zt, xt, _, _ = fo.synthetic_crops(4)
-    x = xt.cuda().repeat(2, 1, 1, 1)[:7]
-    zf = net.get_features(zt.cuda()).repeat(2, 1, 1, 1)[:7]
-    ref = net.track(x, zf)
-    net.set_option("early_sub", "2")
-    try:
-        out = net.track(x, zf)
-        zf2 = net.get_features(zt.cuda())
-    finally:
-        net.set_option("early_sub", "0")
-    assert torch.equal(out[R], ref[R]) and torch.equal(out[C], ref[C])
-    assert torch.equal(zf2, zf[:4])
-
-
-def test_fused_expand_depthwise_blocks(net, sd64):
-    """Optional fused pw-expand + depthwise kernels (stride-2 blocks): same activations as the unfused path."""
-    _, xt, _, _ = fo.synthetic_crops(2)
-    col = {}
-    fo.get_features(sd64, xt.double(), col)
-    net.set_option("fuse", "1")
-    try:
-        got = {n: net.backbone_prefix(xt.cuda(), i).cpu().numpy() for n, i in (("xif2_0", 2), ("xif3_0", 5), ("xif4_0", 9))}
-    finally:
-        net.set_option("fuse", "0")
-    for name, a in got.items():
-        e1, e2 = map_errors(a, col[name].numpy())
-        assert e2 < 2e-5, (name, e1, e2)
 
 
 def test_fused_stem_block_is_bit_identical(net):
@@ -292,33 +261,11 @@ def test_fused_stem_block_is_bit_identical(net):
         assert torch.equal(a, b)
 
 
-def test_constant_bank_small_layers_are_bit_identical(net):
-    """Tiny 1x1 layers with their weights passed by value (constant bank) == the shared-memory broadcast kernels."""
-    zt, xt, _, _ = fo.synthetic_crops(3)
-    ref = []
-    for fuse in ("1", "0"):  # with the unfused stem the 16 -> 16 layer of xif1_0 also runs through this kernel
-        net.set_option("fuse_stem", fuse)
-        net.set_option("small_const", "0")
-        try:
-            plain = [net.get_features(zt.cuda()), net.get_features(xt.cuda())]
-            net.set_option("small_const", "1")
-            const = [net.get_features(zt.cuda()), net.get_features(xt.cuda())]
-        finally:
-            net.set_option("small_const", "1")
-            net.set_option("fuse_stem", "1")
-        for a, b in zip(plain, const):
-            assert torch.equal(a, b)
-        ref.append(const)
-    for a, b in zip(*ref):
-        assert torch.equal(a, b)
-
-
-@pytest.mark.skipif(os.environ.get("FEAR_TEST_EXPERIMENTAL") != "1", reason="opt-in kernels under development")
 @pytest.mark.parametrize("mask", ["1", "2", "3"])
-def test_experimental_fused_depthwise_pointwise(net, mask):
-    """EXPERIMENTAL (fuse_dwpw): depthwise + 1x1 as one tcgen05 kernel -- bit 0: the 16x16-stage backbone blocks
-    (validated bit-identical on B200 in round 1), bit 1: the head's SepConvs (not yet run on hardware).  The depthwise
-    values are computed in the same order as dw_tma_kernel, so nothing may change by a bit."""
+def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
+    """fuse_dwpw (optional): depthwise + 1x1 as one tcgen05 kernel -- bit 0: the 16x16-stage backbone blocks, bit 1:
+    the head's SepConvs.  The depthwise values are computed in the same order as dw_tma_kernel, so nothing may
+    change by a bit."""
     zt, xt, _, _ = fo.synthetic_crops(3)
     zf = net.get_features(zt.cuda())
     ref_f = net.get_features(xt.cuda())
@@ -348,3 +295,151 @@ def test_uint8_input_path_is_bit_identical(net):
     rec = net.boxes_to_numpy(boxes)
     ref = net.boxes_to_numpy(net.track_boxes(xt.cuda(), zf_host))
     assert (rec == ref).all()
+
+
+# ------------------------------------------------------------------------------------------ round 2
+def test_corr_concat_workspace_form():
+    """fear_corr_concat_ws_f32 (tcgen05 kernel, caller's scratch) == fear_corr_concat_f32 (direct kernel) == oracle."""
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(11)
+    B, Bz = 6, 6
+    z = torch.randn(Bz, 256, 64, generator=g)
+    x = torch.randn(B, 256, 16, 16, generator=g)
+    ref = fo.pixelwise_correlation(z.double(), x.double())
+    need = lib.fear_corr_concat_workspace_bytes(B, Bz)
+    assert need == (B * 256 * 320 + Bz * 64 * 256) * 4
+    ws = torch.empty(need // 4 + 256, device="cuda")
+    off = (-ws.data_ptr()) % 1024
+    out = torch.empty(B, 320, 16, 16, device="cuda")
+    zc, xc = z.cuda(), x.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.fear_corr_concat_ws_f32(zc.data_ptr(), Bz, xc.data_ptr(), B, out.data_ptr(), ws.data_ptr() + off,
+                                           need, st), "fear_corr_concat_ws_f32")
+    assert torch.equal(out[:, :256].cpu(), x)
+    assert map_errors(out[:, 256:].cpu().numpy(), ref[:, 256:].numpy())[1] < 1e-5
+    assert lib.fear_corr_concat_ws_f32(zc.data_ptr(), Bz, xc.data_ptr(), B, out.data_ptr(), ws.data_ptr() + off,
+                                       need - 4, st) != 0  # too small a workspace is refused, never grown
+
+
+def test_update_branch_matches_reference(net):
+    """f4: BoxTower.forward(search, kernel, update) -- the cls branch correlates with the dynamic template
+    (reference blocks.py:174-179); golden recorded from the reference's own source in float64."""
+    g = golden("update_branch.npz")
+    zf, xf, uf = (torch.from_numpy(g[k]).float().cuda() for k in ("zf", "xf", "uf"))
+    bbox, cls, cls_dw, x_reg = net.connect_model(xf, zf, uf)
+    assert_maps_close(bbox.cpu().numpy(), g["bbox"], "bbox (update)")
+    assert_maps_close(cls.cpu().numpy(), g["cls"], "cls (update)")
+    assert cls.flatten(1).argmax(1).tolist() == torch.from_numpy(g["cls"]).flatten(1).argmax(1).tolist()
+    b1, c1, _, _ = net.connect_model(xf, zf[:1], uf[:1])
+    assert_maps_close(b1.cpu().numpy(), g["bbox_b1"], "bbox (update, Bz = Bu = 1)")
+    assert_maps_close(c1.cpu().numpy(), g["cls_b1"], "cls (update, Bz = Bu = 1)")
+    # update = None stays the plain head; the regression branch never sees the update template
+    plain = net.connect_model(xf, zf)
+    assert torch.equal(plain[0], bbox) and not torch.equal(plain[1], cls)
+
+
+def test_batch256_parity_and_host_path(net):
+    """The benchmarked configuration (BASELINE config 2: 256 frames on one GPU, 6.9 tile rounds x 148 persistent
+    CTAs): every frame's decoded record vs the fp64 oracle on a strided 32-frame subset, bit-equality of the first
+    frames with the small-batch result, and the pinned-host entry point."""
+    B = 256
+    zt, xt, zu, xu = fo.synthetic_crops(B)
+    net.reserve(B)
+    zf = net.get_features(zt.cuda())
+    boxes, maps = net.track_boxes(xt.cuda(), zf, with_maps=True)
+    rec = net.boxes_to_numpy(boxes)
+    small = net.track(xt[:4].cuda(), zf[:4])
+    assert torch.equal(small[R], maps[R][:4]) and torch.equal(small[C], maps[C][:4])
+    xu_host = xu.permute(0, 2, 3, 1).contiguous().pin_memory()
+    hb = net.boxes_to_numpy(net.track_boxes_from_host(xu_host, zf.cpu().pin_memory()))
+    torch.cuda.synchronize()
+    assert (hb == rec).all()
+    sd64 = fo.to_dtype({k: v for k, v in load_full_state().items() if v.is_floating_point()}, torch.float64)
+    idx = torch.arange(5, B, 8)  # 32 frames: 5, 13, ..., 253
+    with torch.no_grad():
+        ref = fo.track(sd64, xt[idx].double(), fo.get_features(sd64, zt[idx].double()))
+    bbox, coords = fo.decode(ref[R], ref[C])
+    margin = ref[C].flatten(1).topk(2, dim=1).values
+    margin = (margin[:, 0] - margin[:, 1]).numpy()
+    worst = {}
+    for key in (R, C):
+        worst[key] = map_errors(maps[key][idx.cuda()].cpu().numpy(), ref[key].numpy())
+        assert max(worst[key]) <= TOL, (key, worst[key])
+    for j, i in enumerate(idx.tolist()):
+        if margin[j] < 1e-4:
+            continue  # tie at fp32 resolution (reported below), SURVEY.md 8(c)
+        assert (int(rec["row"][i]), int(rec["col"][i])) == tuple(coords[j]), (i, margin[j])
+        got = np.array([rec["x"][i], rec["y"][i], rec["w"][i], rec["h"][i]])
+        np.testing.assert_allclose(got, bbox[j].numpy(), rtol=1e-3, atol=2e-2)
+    _dump("batch256_parity.json", {"frames": len(idx), "reg": worst[R], "cls": worst[C],
+                                   "min_margin": float(margin.min()), "ties": int((margin < 1e-4).sum())})
+
+
+def test_smooth_tracker_matches_reference_trajectory(net):
+    """f4: FEARTracker with ``smooth: true`` (scale / ratio penalty, cosine window, size smoothing -- reference
+    base_tracker.py:126-205) over the first 120 frames of the demo clip vs the reference's own trajectory."""
+    g = golden("smooth_tracker.npz")
+    frames = fo.read_video_rgb(os.path.join(GOLDEN, "test.mp4"))[: len(g["trajectory"]) + 1]
+    trk = fb.FEARTracker(net, cuda_id=0, smooth=True, **fb.FEAR_XS_TRACKER_KWARGS)
+    trk.initialize(frames[0], g["init_bbox"])
+    traj = np.array([list(map(int, trk.update(f)["bbox"])) for f in frames[1:]], dtype=np.int64)
+    same = (traj == g["trajectory"]).all(1)
+    _dump("smooth_trajectory.json", {"frames": int(len(traj)), "identical": int(same.sum())})
+    assert same[:20].all() and same.mean() > 0.9, (int(same.sum()), int(np.argmin(same)))
+
+
+def test_cuda_graph_survives_workspace_growth(net):
+    """a batched call that re-allocates the library workspace must invalidate the tracker's captured
+    CUDA graph (generation counter) instead of replaying into freed buffers."""
+    g = golden("video_teacher.npz")
+    frames = fo.read_video_rgb(os.path.join(GOLDEN, "test.mp4"))[:12]
+    n2 = fb.FEARNet(**fb.FEAR_XS_MODEL_KWARGS)
+    n2.load_state_dict(load_full_state(), strict=True)
+    n2 = n2.cuda().eval()
+    trk = fb.FEARTracker(n2, cuda_id=0, **fb.FEAR_XS_TRACKER_KWARGS)
+    trk.initialize(frames[0], g["init_bbox"])
+    out = [list(map(int, trk.update(f)["bbox"])) for f in frames[1:5]]
+    assert trk._stream_state["graph"] is not None
+    gen = n2.generation()
+    zt, xt, _, _ = fo.synthetic_crops(12)
+    n2.track(xt.cuda(), n2.get_features(zt.cuda()))  # batch 12 > reserved: workspace is freed and re-allocated
+    assert n2.generation() != gen
+    out += [list(map(int, trk.update(f)["bbox"])) for f in frames[5:]]
+    assert out == g["trajectory"][: len(out)].tolist()
+    n2.eval()  # eval() -> eval() keeps the packed handle (no re-fold, no graph invalidation)
+    assert n2.generation() is not None and n2.generation()[0] == n2._handle.value
+
+
+def test_reference_demo_flow_through_compat(net, tmp_path):
+    """f2: the statements of the reference's demo_video.py (imports + get_tracker + track, demo_video.py:1-29) run
+    unchanged against the stand-in modules and the hydra-style config tree."""
+    import subprocess
+    import sys
+
+    script = tmp_path / "demo_like.py"
+    script.write_text(
+        "import numpy as np\n"
+        "from fire import Fire\n"
+        "from hydra.utils import instantiate\n"
+        "from model_training.tracker.fear_tracker import FEARTracker\n"
+        "from model_training.utils.hydra import load_hydra_config_from_path\n"
+        "import imageio.v3 as iio\n"
+        "def main(config_path, video_path, n=8):\n"
+        "    config = load_hydra_config_from_path(config_path=config_path, config_name='fear_tracker')\n"
+        "    model = instantiate(config['model'])\n"
+        "    import bench\n"
+        "    model.load_state_dict(bench.load_state(), strict=True)\n"
+        "    tracker: FEARTracker = instantiate(config['tracker'], model=model.cuda().eval())\n"
+        "    video = iio.imread(video_path)\n"
+        "    tracker.initialize(video[0], np.array([163, 53, 45, 174]))\n"
+        "    print('BOXES', [list(map(int, tracker.update(f)['bbox'])) for f in video[1:n + 1]])\n"
+        "if __name__ == '__main__':\n"
+        "    Fire(main)\n")
+    root = os.path.dirname(os.path.dirname(GOLDEN))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_script.py"), str(script),
+                           "--config_path=" + os.path.join(root, "feartracker_b200", "config"),
+                           "--video_path=" + os.path.join(GOLDEN, "test.mp4")], capture_output=True, text=True,
+                          timeout=300, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = [l for l in proc.stdout.splitlines() if l.startswith("BOXES ")][-1]
+    assert json.loads(line[6:]) == golden("video_teacher.npz")["trajectory"][:8].tolist()

@@ -105,6 +105,30 @@ def test_video_prefix_trajectory(state_dict, golden_dir):
         assert list(box) == g["trajectory"][i - 1].tolist(), i
 
 
+def test_update_branch_golden(state_dict):
+    """BoxTower.forward(search, kernel, update) (blocks.py:174-179) vs the reference's float64 output."""
+    g = golden("update_branch.npz")
+    sd64 = fo.to_dtype(state_dict, torch.float64)
+    zf, xf, uf = (torch.from_numpy(g[k]) for k in ("zf", "xf", "uf"))
+    bbox, cls, _, _ = fo.box_tower(sd64, xf, zf, uf)
+    np.testing.assert_allclose(bbox.numpy(), g["bbox"], rtol=1e-9)
+    np.testing.assert_allclose(cls.numpy(), g["cls"], rtol=1e-9, atol=1e-11)
+    plain = fo.box_tower(sd64, xf, zf)
+    assert torch.equal(plain[0], bbox) and not torch.equal(plain[1], cls)  # only the cls branch sees `update`
+
+
+def test_smooth_tracker_prefix_trajectory(state_dict, golden_dir):
+    """``smooth: true`` (base_tracker.py:126-205): first 25 frames reproduce the reference trajectory."""
+    import os
+
+    g = golden("smooth_tracker.npz")
+    frames = fo.read_video_rgb(os.path.join(golden_dir, "test.mp4"))[:26]
+    trk = fo.OracleTracker(state_dict, dict(fo.TRACKER_CONFIG, smooth=True))
+    trk.initialize(frames[0], g["init_bbox"])
+    for i in range(1, 26):
+        assert list(trk.update(frames[i])["bbox"]) == g["trajectory"][i - 1].tolist(), i
+
+
 @pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present (GPU box)")
 def test_restatement_equals_reference_source(state_dict):
     """Build container only: oracle == the reference's own FEARNet, bit-for-bit (fp32)."""
