@@ -15,6 +15,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_dw_tma.cuh"
 #include "kernels_stem_fused.cuh"
+#include "kernels_irf_fused.cuh"
 
 using namespace fear;
 
@@ -111,6 +112,7 @@ struct FearContext {
   int device = 0;
   Options opt;
   float* d_weights = nullptr;
+  float* d_irf_image = nullptr;  // packed shared-memory weights image of the fused xif2_0 kernel
   std::vector<float> h_weights;  // host mirror of d_weights (device layout)
   const float *stem_w = nullptr, *stem_b = nullptr;
   BlockW blocks[kNumBlocks];
@@ -361,6 +363,21 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
     const IrfSpec& sp = kBlocks[i];
     const BlockW& bw = c->blocks[i];
     const int M = B * h * w;
+    if (i == 1 && c->opt.fuse_irf && tc::available() && effective(c->opt.pw) == IMPL_TC && c->d_irf_image) {
+      // xif2_0: expand 1x1 -> depthwise 3x3 s2 -> project 1x1 in ONE kernel; the expanded tensor stays on the SM
+      LaunchScope scope(c, ST_BACKBONE_PW, s);
+      int r = tc::launch_irf_s2(s, X, Y, c->d_irf_image, B, h, w);
+      if (r < 0) return set_err(FEAR_EINVAL, "fused IRF block launch failed (%d)", r);
+      if (r == 0) {
+        FEAR_TRY(check_launch("tc::irf_s2_fused_kernel"));
+        h /= 2;
+        w /= 2;
+        float* t = X;
+        X = Y;
+        Y = t;
+        continue;
+      }
+    }
     const float* E = X;
     if (sp.has_pw()) {
       FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), M, 1));
@@ -723,6 +740,22 @@ extern "C" int fear_pack_weights(const float* blob, const uint64_t* offsets, int
     for (int o = 0; o < 16; ++o)
       for (int k = 0; k < 16; ++k) c->fs.pw[k * 16 + o] = pw[o * 16 + k];
     memcpy(c->fs.pb, host_of(b0.pwl.b), sizeof(c->fs.pb));
+    // fused xif2_0 kernel (kernels_irf_fused.cuh): its weights as one shared-memory image
+    const BlockW& b1 = c->blocks[1];
+    if (kBlocks[1].cin != tc::kIrfCin || kBlocks[1].mid() != tc::kIrfMid || kBlocks[1].cout != tc::kIrfCout ||
+        kBlocks[1].k != 3 || kBlocks[1].stride != 2) {
+      fear_free(c);
+      return set_err(FEAR_ESTATE, "internal: irf_s2_fused_kernel is specialised for xif2_0 (16 -> 96 -> 24, 3x3 s2)");
+    }
+    std::vector<float> img(tc::kIrfImageFloats);
+    tc::irf_build_image(img.data(), host_of(b1.pw.w_hi), host_of(b1.pw.w_lo), host_of(b1.pwl.w_hi), host_of(b1.pwl.w_lo),
+                        host_of(b1.dw.w), host_of(b1.pw.b), host_of(b1.dw.b), host_of(b1.pwl.b));
+    e = cudaMalloc(&c->d_irf_image, img.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_irf_image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      fear_free(c);
+      return set_err((int)e, "upload of the fused-block weights failed: %s", cudaGetErrorString(e));
+    }
   }
   *handle = c;
   int r = fear_reserve(c, 1);
@@ -797,6 +830,7 @@ extern "C" void fear_free(FearContext* c) {
   }
   if (c->ws) cudaFree(c->ws);
   if (c->d_weights) cudaFree(c->d_weights);
+  if (c->d_irf_image) cudaFree(c->d_irf_image);
   delete c;
 }
 
@@ -1023,26 +1057,10 @@ extern "C" int fear_debug_backbone_prefix(FearContext* c, const float* d_img, in
     stem_conv3x3s2_kernel<false><<<blocks, 128, 0, s>>>(d_img, c->stem_w, c->stem_b, c->bufX, B, H, W, StemNorm());
     FEAR_TRY(check_launch("stem_conv3x3s2_kernel"));
   }
-  int h = H / 2, w = W / 2, ch = kStemC;
-  float *X = c->bufX, *Y = c->bufY;
-  for (int i = 0; i < nblocks; ++i) {
-    const IrfSpec& sp = kBlocks[i];
-    const BlockW& bw = c->blocks[i];
-    const float* E = X;
-    if (sp.has_pw()) {
-      FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, X, sp.cin, bw.pw, nullptr, 0, c->bufE, sp.mid(), B * h * w, 1));
-      E = c->bufE;
-    }
-    FEAR_TRY(launch_dw(c, ST_BACKBONE_DW, s, E, bw.dw, c->bufD, B, h, w, sp.stride, true));
-    h /= sp.stride;
-    w /= sp.stride;
-    FEAR_TRY(launch_pw(c, ST_BACKBONE_PW, s, c->bufD, sp.mid(), bw.pwl, sp.residual() ? X : nullptr, sp.cout, Y,
-                       sp.cout, B * h * w, 0));
-    float* t = X;
-    X = Y;
-    Y = t;
-    ch = sp.cout;
-  }
+  int h = H / 2, w = W / 2;
+  float* X = nullptr;
+  FEAR_TRY(run_blocks(c, s, c->bufX, B, h, w, 0, nblocks, &X));
+  const int ch = nblocks ? kBlocks[nblocks - 1].cout : kStemC;
   const int P = h * w;
   return launch_transpose(c, s, X, ch, (long long)P * ch, d_out, P, (long long)ch * P, P, ch, B);
 }

@@ -98,6 +98,45 @@ def corr_perf(lib, impl, B=256, iters=50):
     return {"impl": impl, "us": us, "GBps": 393216 * B / us * 1e-3}
 
 
+def irf_case(B):
+    """Fused xif2_0 kernel (expand -> depthwise s2 -> project in one launch) vs the three-kernel path (must be
+    bit-identical) and vs the fp64 oracle, on search- and template-sized inputs; B frames so that every persistent
+    CTA walks several tiles."""
+    import feartracker_b200 as fb
+    from oracle import fear_oracle as fo
+    from tests.helpers import load_full_state, map_errors
+
+    sd = load_full_state()
+    net = fb.FEARNet(**fb.FEAR_XS_MODEL_KWARGS)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.reserve(B)
+    sd64 = fo.to_dtype({k: v for k, v in sd.items() if v.is_floating_point()}, torch.float64)
+    res = {"B": B}
+    for name, size in (("search", 256), ("template", 128)):
+        g = torch.Generator().manual_seed(B + size)
+        x = torch.randn(B, 3, size, size, generator=g)
+        net.set_option("fuse_irf", "0")
+        ref = net.backbone_prefix(x.cuda(), 2)
+        ref_full = net.get_features(x.cuda())
+        net.set_option("fuse_irf", "1")
+        got = net.backbone_prefix(x.cuda(), 2)
+        got_full = net.get_features(x.cuda())
+        torch.cuda.synchronize()
+        diff = (got - ref).abs()
+        col = {}
+        fo.get_features(sd64, x[:2].double(), col)
+        res[name] = {
+            "bit_identical": bool(torch.equal(got, ref)), "features_bit_identical": bool(torch.equal(got_full, ref_full)),
+            "max_abs_diff": float(diff.max()), "ref_absmax": float(ref.abs().max()),
+            "worst_frame": int(diff.flatten(1).amax(1).argmax()),
+            "per_frame_max": diff.flatten(1).amax(1).tolist()[:8],
+            "vs_oracle": map_errors(got[:2].cpu().numpy(), col["xif2_0"].numpy()),
+            "unfused_vs_oracle": map_errors(ref[:2].cpu().numpy(), col["xif2_0"].numpy()),
+        }
+    return res
+
+
 def main():
     mode = sys.argv[1]
     lib = _lib.init(0)
@@ -112,6 +151,8 @@ def main():
         res["perf"] = [corr_perf(lib, impl) for impl in sys.argv[2:]]
     elif mode == "net":
         res.update(net_case(sys.argv[2], sys.argv[3]))
+    elif mode == "irf":
+        res.update(irf_case(int(sys.argv[2]) if len(sys.argv) > 2 else 16))
     print("TC_CHECK " + json.dumps(res), flush=True)
 
 

@@ -42,3 +42,14 @@ def test_network_with_tensor_core_kernels(pw, corr):
     assert res["reg"][0] <= 1e-3 and res["reg"][1] <= 1e-3, res
     assert res["cls"][0] <= 1e-3 and res["cls"][1] <= 1e-3, res
     assert res["argmax_same"]
+
+
+@pytest.mark.parametrize("B", [2, 19])
+def test_fused_irf_block(B):
+    """xif2_0 as one tcgen05 kernel (expanded tensor on-chip): bit-identical to the three-kernel path, <= 2e-5 of the
+    fp64 oracle; B = 19 gives every persistent CTA several tiles (608 search tiles on 148 CTAs)."""
+    res = _run("irf", B, timeout=400)
+    for name in ("search", "template"):
+        r = res[name]
+        assert r["vs_oracle"][1] < 2e-5, (name, r)
+        assert r["bit_identical"] and r["features_bit_identical"], (name, r)
