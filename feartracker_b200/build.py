@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
         raise RuntimeError("nvcc not found: cannot build libfear_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *SOURCES]
+    extra = os.environ.get("FEAR_NVCC_FLAGS", "").split()  # build-time only (profiling builds); nothing is read at run time
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

@@ -113,6 +113,7 @@ struct FearContext {
   Options opt;
   float* d_weights = nullptr;
   float* d_irf_image = nullptr;  // packed shared-memory weights image of the fused xif2_0 kernel
+  unsigned long long* d_irf_dbg = nullptr;  // FEAR_IRF_TIMING builds only
   std::vector<float> h_weights;  // host mirror of d_weights (device layout)
   const float *stem_w = nullptr, *stem_b = nullptr;
   BlockW blocks[kNumBlocks];
@@ -366,7 +367,7 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
     if (i == 1 && c->opt.fuse_irf && tc::available() && effective(c->opt.pw) == IMPL_TC && c->d_irf_image) {
       // xif2_0: expand 1x1 -> depthwise 3x3 s2 -> project 1x1 in ONE kernel; the expanded tensor stays on the SM
       LaunchScope scope(c, ST_BACKBONE_PW, s);
-      int r = tc::launch_irf_s2(s, X, Y, c->d_irf_image, B, h, w);
+      int r = tc::launch_irf_s2(s, X, Y, c->d_irf_image, B, h, w, c->d_irf_dbg);
       if (r < 0) return set_err(FEAR_EINVAL, "fused IRF block launch failed (%d)", r);
       if (r == 0) {
         FEAR_TRY(check_launch("tc::irf_s2_fused_kernel"));
@@ -989,6 +990,17 @@ extern "C" int fear_forward(FearContext* c, const float* d_template, const float
   return track_impl(c, (cudaStream_t)stream, d_template, d_search, nullptr, B, B, d_bbox, d_cls, d_boxes);
 }
 
+// Context crop + padding + bilinear resize on the device (get_extended_crop of the tracking loop; see
+// crop_resize_u8_kernel).  d_params: 8 + 6 * out_size int32 (layout in kernels_ffma.cuh / include/fear_b200.h).
+extern "C" int fear_crop_resize_u8(const uint8_t* d_frame, int H, int W, const int32_t* d_params, uint8_t* d_crop,
+                                   int out_size, void* stream) {
+  if (!d_frame || !d_params || !d_crop || H < 1 || W < 1 || out_size < 1 || out_size > 1024)
+    return set_err(FEAR_EINVAL, "bad argument");
+  const int n = out_size * out_size;
+  crop_resize_u8_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_frame, H, W, d_params, d_crop, out_size);
+  return check_launch("crop_resize_u8_kernel");
+}
+
 extern "C" int fear_decode(const float* d_bbox, const float* d_cls, int B, int apply_sigmoid, FearBox* d_boxes,
                            void* stream) {
   if (!d_bbox || !d_cls || !d_boxes || B < 1) return set_err(FEAR_EINVAL, "bad argument");
@@ -1124,6 +1136,23 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   else return set_err(FEAR_EINVAL, "unknown option '%s' (corr | pw)", key);
   return 0;
 }
+
+#ifdef FEAR_IRF_TIMING
+// Profiling build only (python -m feartracker_b200.build with FEAR_NVCC_FLAGS=-DFEAR_IRF_TIMING; not declared in the
+// public header): per-warp cycle counters of the last irf_s2_fused_kernel launch, [148][8 warps][8] uint64.
+extern "C" int fear_debug_irf_timing(FearContext* c, unsigned long long* host_out, int n) {
+  if (!c || !host_out) return FEAR_EINVAL;
+  DeviceGuard guard(c->device);
+  if (!c->d_irf_dbg) {
+    CUDA_TRY(cudaMalloc(&c->d_irf_dbg, 148 * 128 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_irf_dbg, 0, 148 * 128 * sizeof(unsigned long long)));
+    return 1;  // armed: run a step, then call again
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(host_out, c->d_irf_dbg, sizeof(unsigned long long) * (n < 148 * 128 ? n : 148 * 128), cudaMemcpyDeviceToHost));
+  return 0;
+}
+#endif
 
 extern "C" int64_t fear_launch_count(const FearContext* c) { return c ? c->launches : 0; }
 extern "C" int64_t fear_generation(const FearContext* c) { return c ? c->generation : -1; }

@@ -379,6 +379,45 @@ __global__ void __launch_bounds__(256) gemm_nt_ffma_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Context crop + constant-colour padding + bilinear resize of the tracking loop, on the device
+// (reference model_training/utils/utils.py:215-253 get_extended_crop: cv2.copyMakeBorder + albumentations.Resize =
+// cv2.resize(INTER_LINEAR) on uint8).  The frame is uploaded once; this kernel reads the context window straight out
+// of it (pixels outside the frame = the padding colour) and reproduces OpenCV's 8-bit fixed-point bilinear kernel
+// bit for bit: 11-bit coefficients, horizontal pass in int32, vertical pass
+//     ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2
+// (cv::VResizeLinear<uchar> / VResizeLinearVec_32s8u).  The per-axis source offsets and coefficients are computed on
+// the host in float32 exactly as cv::resize does (feartracker_b200/image_ops.py:resize_tables) and passed in
+// `params`:  [0..3] context x, y, w, h (frame coordinates, may leave the frame); [4..6] padding colour RGB; [7] unused;
+// then xofs[S], xa0[S], xa1[S], yofs[S], ya0[S], ya1[S] for an S x S output.  out: [S][S][3] uint8 (HWC).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __restrict__ frame, int H, int W,
+                                                             const int* __restrict__ params, uint8_t* __restrict__ out,
+                                                             int S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * S) return;
+  const int dy = idx / S, dx = idx - dy * S;
+  const int cx = __ldg(params), cy = __ldg(params + 1), cw = __ldg(params + 2), ch = __ldg(params + 3);
+  const int* tx = params + 8;
+  const int* ty = params + 8 + 3 * S;
+  const int x0 = __ldg(tx + dx), a0 = __ldg(tx + S + dx), a1 = __ldg(tx + 2 * S + dx);
+  const int yo = __ldg(ty + dy), b0 = __ldg(ty + S + dy), b1 = __ldg(ty + 2 * S + dy);
+  const int x1 = min(x0 + 1, cw - 1);
+  const int y0 = min(max(yo, 0), ch - 1), y1 = min(max(yo + 1, 0), ch - 1);
+  int pad[3] = {__ldg(params + 4), __ldg(params + 5), __ldg(params + 6)};
+  auto px = [&](int y, int x, int c) -> int {  // padded context window
+    const int fy = cy + y, fx = cx + x;
+    return (fy >= 0 && fy < H && fx >= 0 && fx < W) ? (int)__ldg(frame + ((long long)fy * W + fx) * 3 + c) : pad[c];
+  };
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s0 = px(y0, x0, c) * a0 + px(y0, x1, c) * a1;
+    const int s1 = px(y1, x0, c) * a0 + px(y1, x1, c) * a1;
+    const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    out[(long long)idx * 3 + c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Pixel-wise correlation straight on the reference's layouts (MobileCorrelation.forward, blocks.py:121-123):
 //   out[b, 256 + k, p] = sum_c z[b, c, k] * x[b, c, p],  z (Bz,256,64), x (B,256,256), out (B,320,256).
 // Compatibility kernel of the workspace-free C entry point fear_corr_concat_f32; the hot path runs

@@ -13,9 +13,11 @@
 //                      64 B each) straight from global memory one tile AHEAD, split them into tf32 (hi, lo) and park
 //                      them in TENSOR MEMORY as the A operand of the expand GEMM (5 M-tiles x (16 + 16) columns):
 //                      X never touches shared memory.  They also run the project epilogue (+b2, store Y).
-//   MMA thread         expand: per 32-channel slab c and M-tile i, D[128 x 32] = A_i * W1[c]^T as 3xTF32 with the A
-//                      operand in TMEM ("TS" form) into a ring of eight 32-column TMEM accumulators;
-//                      project: acc2[128 x 24] += dw_c * W2[:, c]^T (A = depthwise output tile in smem, hi/lo).
+//   MMA threads (4)    warps 0-2 -- expand, one issuer per 32-channel slab c: per M-tile i, D[128 x 32] = A_i * W1[c]^T
+//                      as 3xTF32 with the A operand in TMEM ("TS" form) into a ring of eight 32-column TMEM
+//                      accumulators;  warp 3 -- project: acc2[128 x 24] += dw_c * W2[:, c]^T (A = depthwise output
+//                      tile in smem, hi/lo).  Several issuers because ONE thread's instruction latency (waits +
+//                      descriptors + 6 MMAs per unit), not the tensor pipe, bounded the first version.
 //   worker groups (2x4 warps)  take alternate slabs: (1) expand epilogue TMEM -> +b1, ReLU, zero outside the image
 //                      (the depthwise conv zero-pads E, and E(0) = relu(b1) != 0) -> 561 x 32-channel fp32 slab in
 //                      shared memory; (2) depthwise 3x3 stride 2 out of that slab (packed FFMA2, same FMA order
@@ -25,8 +27,11 @@
 // All MMA orders / operand splits / epilogue additions replicate pw_tc_kernel, so the block is bit-identical to the
 // three-kernel path (tests/test_gpu_parity.py::test_fused_irf_block_is_bit_identical).
 //
-// TMEM (512 columns): [0,160) A operand (5 x (16 hi + 16 lo)); [160,416) 8 expand accumulators x 32;
-// [416,448) project main, [448,480) project correction accumulator.
+// TMEM (512 columns): [0,160) A operand (5 x (16 hi + 16 lo)); [160,448) 3 slabs x 3-deep ring of 32-column expand
+// accumulators (a ring per issuer: mbarrier parity waits are only safe when producer and consumer of a slot can be
+// at most one phase apart, which in-order use by ONE issuer guarantees); [448,480) project main, [480,512) project
+// correction accumulator.
+// (tile order and barrier protocol: DESIGN.md section 4.4)
 // smem: A2 (hi, lo) 32 KB | weights image 40.25 KB (W1 [hi|lo] rows, W2 [hi;lo] x 3 chunks, dw, biases) | barriers |
 // 2 x 70.1 KB slabs = 214 KB.
 #pragma once
@@ -42,8 +47,8 @@ constexpr int kIrfPix = kIrfIH * kIrfIW;                        // 561
 constexpr int kIrfMT = (kIrfPix + 127) / 128;                   // 5 M-tiles of the expand GEMM
 constexpr int kIrfSlabs = kIrfMid / 32;                         // 3
 constexpr int kIrfUnitsPerTile = kIrfSlabs * kIrfMT;            // 15
-constexpr int kIrfRing = 8;                                     // expand accumulator ring (TMEM)
-constexpr int kIrfThreads = 512;                                // 16 warps: MMA, 3 spare, 4 loader, 2 x 4 workers
+constexpr int kIrfRing = 3;                                     // expand accumulator ring PER SLAB ISSUER (TMEM): 9 slots
+constexpr int kIrfThreads = 512;                                // 16 warps: 4 MMA issuers, 4 loader, 2 x 4 workers
 
 // weights image (floats), copied verbatim into shared memory
 constexpr int kIrfW1Floats = kIrfMid * 32;                        // [96 rows][hi 16 | lo 16], SWIZZLE_128B
@@ -60,13 +65,13 @@ constexpr int kIrfOffB1 = kIrfOffDw + kIrfDwFloats * 4;
 constexpr int kIrfOffBd = kIrfOffB1 + kIrfMid * 4;
 constexpr int kIrfOffB2 = kIrfOffBd + kIrfMid * 4;
 constexpr int kIrfOffBars = ((kIrfOffB2 + kIrfCoutPad * 4 + 255) / 256) * 256;
-constexpr int kIrfOffSlab = kIrfOffBars + 256;
+constexpr int kIrfOffSlab = kIrfOffBars + 512;  // 33 mbarriers + the TMEM base slot
 constexpr int kIrfSlabBytes = kIrfPix * 128;
 constexpr int kIrfSmemBytes = kIrfOffSlab + 2 * kIrfSlabBytes + 1024 /*alignment slack*/;
 static_assert(kIrfSmemBytes <= 232448, "fused IRF kernel exceeds the 227 KB shared-memory limit");
 static_assert(kIrfOffW1 % 1024 == 0 && kIrfOffW2 % 1024 == 0, "UMMA tiles must be 1024-byte aligned");
 
-constexpr int kIrfColA = 0, kIrfColAcc = 160, kIrfColP = 416;  // TMEM column map
+constexpr int kIrfColA = 0, kIrfColAcc = 160, kIrfColP = 448;  // TMEM column map
 constexpr int kIrfTmemCols = 512;
 
 struct IrfParams {
@@ -75,7 +80,16 @@ struct IrfParams {
   const float* image;  // kIrfImageFloats packed weights (device)
   int B, H, W;         // input map
   int tiles_x, tiles_y, num_tiles;
+  unsigned long long* dbg;  // FEAR_IRF_TIMING builds only: [grid][8 worker warps][8] cycle counters, else null
 };
+
+#ifdef FEAR_IRF_TIMING
+#define IRF_T(var) const long long var = clock64()
+#define IRF_ACC(slot, a, b) tacc[slot] += (b) - (a)
+#else
+#define IRF_T(var)
+#define IRF_ACC(slot, a, b)
+#endif
 
 // Host: build the shared-memory weights image.  w1_hi/w1_lo [96][16], w2_hi/w2_lo [24][96] (tf32-split copies the
 // tensor-core path already keeps), dw [9][96] (tap-major), biases.
@@ -119,25 +133,27 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
   extern __shared__ uint8_t irf_smem_raw[];
   uint8_t* smem = irf_smem_raw + ((1024u - (smem_u32(irf_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kIrfOffBars);
-  uint64_t* a_full = bars;                 // A operand of tile t is in TMEM            (4 loader warps)
-  uint64_t* a_empty = bars + 1;            // expand MMAs of the tile have read it      (commit)
-  uint64_t* acc_full = bars + 2;           // [8] expand accumulator complete           (commit)
-  uint64_t* acc_empty = bars + 10;         // [8] drained by the worker group           (4 warps)
-  uint64_t* a2_full = bars + 18;           // depthwise (hi, lo) tile written           (4 warps)
-  uint64_t* a2_empty = bars + 19;          // project MMAs have read it                 (commit)
-  uint64_t* acc2_full = bars + 20;         // project accumulator complete              (commit)
-  uint64_t* acc2_empty = bars + 21;        // drained by the loader warps               (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* a_full = bars;                 // [5] M-tile i of the tile's A operand is in TMEM   (4 loader warps)
+  uint64_t* a_empty = bars + 5;            // [5] the expand MMAs of the tile have read it      (commit)
+  uint64_t* acc_full = bars + 10;          // [9] expand accumulator complete           (commit)
+  uint64_t* acc_empty = bars + 19;         // [9] drained by the worker group           (4 warps)
+  uint64_t* a2_full = bars + 28;           // depthwise (hi, lo) tile written           (4 warps)
+  uint64_t* a2_empty = bars + 29;          // project MMAs have read it                 (commit)
+  uint64_t* acc2_full = bars + 30;         // project accumulator complete              (commit)
+  uint64_t* acc2_empty = bars + 31;        // drained by the loader warps               (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) {
+  if (warp == 4) {
     tmem_alloc(tmem_slot, kIrfTmemCols);
     tmem_relinquish();
   }
-  if (threadIdx.x == 32) {
-    mbar_init(a_full, 4);
-    mbar_init(a_empty, 1);
-    for (int s = 0; s < kIrfRing; ++s) {
+  if (threadIdx.x == 160) {
+    for (int i = 0; i < kIrfMT; ++i) {
+      mbar_init(&a_full[i], 4);
+      mbar_init(&a_empty[i], kIrfSlabs);
+    }
+    for (int s = 0; s < kIrfSlabs * kIrfRing; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
@@ -172,22 +188,60 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
     ox0 = tx * kIrfTW;
   };
 
-  if (warp == 0) {
-    // ===================================== MMA issuer =====================================
+  if (warp < kIrfSlabs) {
+    // ===================================== expand MMA issuers =====================================
+    // One issuing thread per 32-channel slab c = warp (a single thread's instruction latency, not the tensor pipe,
+    // bounded a one-issuer version): its W1 descriptors are loop invariants, it walks the tile's five M-tiles.
     if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t idesc_e = umma_idesc_tf32(128, 32);   // expand: N = 32 channel slab
-      constexpr uint32_t idesc_p = umma_idesc_tf32(128, 32);   // project: a_lo x w_hi
-      constexpr uint32_t idesc_p2 = umma_idesc_tf32(128, 64);  // project: a_hi x [w_hi ; w_lo] -> main | corr
-      const uint32_t w1 = smem_u32(smem + kIrfOffW1), w2 = smem_u32(smem + kIrfOffW2);
+      constexpr uint32_t idesc_e = umma_idesc_tf32(128, 32);  // N = 32-channel slab
+      const int c = warp;
+      const uint32_t brow = smem_u32(smem + kIrfOffW1) + c * 4096;  // rows [32c, 32c + 32) of W1: [hi 64 B | lo 64 B]
+      const uint64_t dbh0 = umma_desc_k_sw128(brow), dbh1 = umma_desc_k_sw128(brow + 32);
+      const uint64_t dbl0 = umma_desc_k_sw128(brow + 64), dbl1 = umma_desc_k_sw128(brow + 96);
+      int n = 0;  // this issuer's unit counter: unit n uses slot c * 3 + n % 3 for the (n / 3)-th time
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int i = 0; i < kIrfMT; ++i, ++n) {
+          mbar_wait_backoff(&a_full[i], (uint32_t)(tl & 1));
+          const int slot = c * kIrfRing + n % kIrfRing;
+          mbar_wait_backoff(&acc_empty[slot], (uint32_t)(((n / kIrfRing) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d = tmem_base + kIrfColAcc + slot * 32;
+          const uint32_t a_hi = tmem_base + kIrfColA + i * 32, a_lo = a_hi + 16;
+          // K = 16 = 2 K-steps x (hi*hi, lo*hi, hi*lo): same product order as pw_tc_kernel's single-accumulator path
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p0, p1;\n\t"
+              "setp.ne.b32 p0, 0, 0;\n\t"
+              "setp.eq.b32 p1, 0, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %7, p0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %7, p1;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %5, %7, p1;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%8], %4, %7, p1;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%9], %4, %7, p1;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%8], %6, %7, p1;\n\t"
+              "}\n" ::"r"(d),
+              "r"(a_hi), "r"(a_lo), "l"(dbh0), "l"(dbh1), "l"(dbl0), "l"(dbl1), "r"(idesc_e), "r"(a_hi + 8), "r"(a_lo + 8)
+              : "memory");
+          tc_commit(&acc_full[slot]);
+          tc_commit(&a_empty[i]);  // (count 3: one commit per slab issuer) this M-tile's A columns may be refilled
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== project MMA issuer =====================================
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t idesc_p = umma_idesc_tf32(128, 32);   // a_lo x w_hi
+      constexpr uint32_t idesc_p2 = umma_idesc_tf32(128, 64);  // a_hi x [w_hi ; w_lo] -> main | corr
+      const uint32_t w2 = smem_u32(smem + kIrfOffW2);
       const uint32_t a2h = smem_u32(smem + kIrfOffA2), a2l = a2h + 16384;
-      const int units = my_tiles * kIrfUnitsPerTile, projects = my_tiles * kIrfSlabs;
-      auto do_project = [&](int pj) {
-        const int tl = pj / kIrfSlabs, c = pj - tl * kIrfSlabs;
+      const int projects = my_tiles * kIrfSlabs;
+      int tl = 0, c = 0;
+      for (int pj = 0; pj < projects; ++pj) {
         if (c == 0) {
-          mbar_wait(acc2_empty, (uint32_t)((tl & 1) ^ 1));
+          mbar_wait_backoff(acc2_empty, (uint32_t)((tl & 1) ^ 1));
           tc_fence_after();
         }
-        mbar_wait(a2_full, (uint32_t)(pj & 1));
+        mbar_wait_backoff(a2_full, (uint32_t)(pj & 1));
         tc_fence_after();
         const uint32_t d = tmem_base + kIrfColP;
         const uint32_t bh = w2 + c * 8192;  // [hi 32 rows ; lo 32 rows] x 128 B
@@ -200,34 +254,11 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
         }
         tc_commit(a2_empty);
         if (c == kIrfSlabs - 1) tc_commit(acc2_full);
-      };
-      int next_project = 0;
-      for (int u = 0; u < units; ++u) {
-        // project pj runs right before expand unit 5 * pj + 13 (see the deadlock analysis in DESIGN.md)
-        if (u >= 13 && (u - 13) % kIrfMT == 0 && next_project < projects) do_project(next_project++);
-        const int tl = u / kIrfUnitsPerTile, ui = u - tl * kIrfUnitsPerTile;
-        const int c = ui / kIrfMT, i = ui - c * kIrfMT;
-        if (ui == 0) {
-          mbar_wait(a_full, (uint32_t)(tl & 1));
-          tc_fence_after();
+        if (++c == kIrfSlabs) {
+          c = 0;
+          ++tl;
         }
-        const int slot = u % kIrfRing;
-        mbar_wait(&acc_empty[slot], (uint32_t)(((u / kIrfRing) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d = tmem_base + kIrfColAcc + slot * 32;
-        const uint32_t a_hi = tmem_base + kIrfColA + i * 32, a_lo = a_hi + 16;
-        const uint32_t brow = w1 + c * 4096;  // rows [32c, 32c + 32) of W1: [hi 64 B | lo 64 B] per row
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {  // K = 16 = 2 K-steps; same product order as pw_tc_kernel's single-accumulator path
-          const uint64_t dbh = umma_desc_k_sw128(brow + j * 32), dbl = umma_desc_k_sw128(brow + 64 + j * 32);
-          mma_tf32_ts(d, a_hi + j * 8, dbh, idesc_e, j != 0);
-          mma_tf32_ts(d, a_lo + j * 8, dbh, idesc_e, 1);
-          mma_tf32_ts(d, a_hi + j * 8, dbl, idesc_e, 1);
-        }
-        tc_commit(&acc_full[slot]);
-        if (ui == kIrfUnitsPerTile - 1) tc_commit(a_empty);
       }
-      while (next_project < projects) do_project(next_project++);
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================================== loader + project epilogue =====================================
@@ -251,7 +282,7 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
     auto project_epilogue = [&](int tl) {
       int b, oy0, ox0;
       tile_coords(tl, b, oy0, ox0);
-      mbar_wait(acc2_full, (uint32_t)(tl & 1));
+      mbar_wait_backoff(acc2_full, (uint32_t)(tl & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + kIrfColP + ((uint32_t)(q * 32) << 16);
       const int oy = oy0 + (row >> 4), ox = ox0 + (row & 15);
@@ -280,10 +311,10 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
     };
     if (my_tiles > 0) prefetch(0);
     for (int tl = 0; tl < my_tiles; ++tl) {
-      mbar_wait(a_empty, (uint32_t)((tl & 1) ^ 1));
-      tc_fence_after();
 #pragma unroll
       for (int i = 0; i < kIrfMT; ++i) {
+        mbar_wait_backoff(&a_empty[i], (uint32_t)((tl & 1) ^ 1));  // the previous tile's MMAs no longer read these columns
+        tc_fence_after();
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -298,11 +329,11 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
         const uint32_t tdst = tmem_base + kIrfColA + i * 32 + ((uint32_t)(q * 32) << 16);
         tmem_st_32x16(tdst, hi);
         tmem_st_32x16(tdst + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[i]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
       if (tl + 1 < my_tiles) prefetch(tl + 1);
       if (tl > 0) project_epilogue(tl - 1);
     }
@@ -314,46 +345,100 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
     const int bar_id = 1 + group;
     const int total_slabs = my_tiles * kIrfSlabs;
     const int cg = lane & 7;
+    const uint32_t lane_base = tmem_base + kIrfColAcc + ((uint32_t)(gw * 32) << 16);
+    // Slab layout: pixel pb = by * 33 + bx of the 17 x 33 box at byte pb * 128; the 16-byte chunk of channel group j
+    // sits at position j ^ (bx & 7): consecutive pixels of a row (= consecutive lanes of the writer) hit different
+    // banks, and a reader's chunk offset depends only on the box column -> five per-thread constants.
+    // Per-thread geometry of the two 2 x 2 output blocks this thread computes (it = 0 / 1):
+    //   block id = it * 16 + gw * 4 + (lane >> 3):  oy_l = (blk >> 3) * 2 (it adds 4), ox_l = (blk & 7) * 2
+    const int blk0 = gw * 4 + (lane >> 3);
+    const int oy_l0 = (blk0 >> 3) * 2, ox_l = (blk0 & 7) * 2;
+    uint32_t col_off[5];  // byte offset of input column 2 * ox_l + i inside a slab row (incl. the channel-group swizzle)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int bx = 2 * ox_l + i;
+      col_off[i] = (uint32_t)(bx * 128 + ((cg ^ (bx & 7)) << 4));
+    }
+    // expand-epilogue geometry per M-tile: box coordinates of this thread's row
+#ifdef FEAR_IRF_TIMING
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // 8 arrive part, 9 prefetch issue, 10 processing, 11 bias loads
+    long long tacc_unused[1] = {0};  // 0 wait acc_full, 1 epilogue, 2 bar (slab done), 3 wait a2_empty,
+                                                   // 4 depthwise, 5 bar (slab free), 6 total
+    const long long t_begin = clock64();
+#endif
     for (int sc = group; sc < total_slabs; sc += 2) {
       const int tl = sc / kIrfSlabs, c = sc - tl * kIrfSlabs;
       int b, oy0, ox0;
       tile_coords(tl, b, oy0, ox0);
+      const bool border = (oy0 == 0) || (ox0 == 0);  // only these tiles have box pixels outside the image
       // ---- (1) expand epilogue: TMEM -> +b1, ReLU, zero outside the image -> slab ----
-      const float4* b1 = reinterpret_cast<const float4*>(smem + kIrfOffB1 + c * 128);
-#pragma unroll 1
-      for (int i = 0; i < kIrfMT; ++i) {
-        const int u = sc * kIrfMT + i;
-        const int slot = u % kIrfRing;
-        mbar_wait(&acc_full[slot], (uint32_t)((u / kIrfRing) & 1));
-        tc_fence_after();
-        const int pb = i * 128 + gw * 32 + lane;
-        if (i * 128 + gw * 32 < kIrfPix) {  // warp-uniform: this warp's 32 rows hold at least one real pixel
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + kIrfColAcc + slot * 32 + ((uint32_t)(gw * 32) << 16), r);
-          tmem_ld_wait();
-          if (pb < kIrfPix) {
-            const int by = pb / kIrfIW, bx = pb - by * kIrfIW;
-            const bool inside = (2 * oy0 - 1 + by) >= 0 && (2 * ox0 - 1 + bx) >= 0;
-            float4* dst = reinterpret_cast<float4*>(slab + pb * 128);
+      // Software pipeline over 10 half-M-tiles (16 accumulator columns each): the TMEM load of half k + 1 is in
+      // flight while half k is biased / clamped / stored; the slab's 32 biases live in registers.
+      float4 bb[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b1[j];
+      for (int j = 0; j < 8; ++j) bb[j] = reinterpret_cast<const float4*>(smem + kIrfOffB1 + c * 128)[j];
+      const int n0 = tl * kIrfMT;  // slab issuer c's unit counter at M-tile 0 of this tile (slot c * 3 + n % 3)
+      uint32_t r[2][16];
+      IRF_T(t0);
+      mbar_wait(&acc_full[c * kIrfRing + n0 % kIrfRing], (uint32_t)((n0 / kIrfRing) & 1));
+      IRF_T(t0b);
+      IRF_ACC(0, t0, t0b);
+      tc_fence_after();
+      tmem_ld_32x16(lane_base + (c * kIrfRing + n0 % kIrfRing) * 32, r[0]);
+#pragma unroll 1
+      for (int i = 0; i < kIrfMT; ++i) {  // (runtime loop: the fully unrolled version thrashed the instruction cache)
+        const int n = n0 + i;
+        const int pb = i * 128 + gw * 32 + lane;
+        const int by = pb / kIrfIW, bx = pb - by * kIrfIW;
+        const int sw = bx & 7;
+        const bool outside = border && ((2 * oy0 - 1 + by) < 0 || (2 * ox0 - 1 + bx) < 0);
+        const uint32_t dst = smem_u32(slab + pb * 128);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld_wait();  // half (i, hh) has landed in r[hh]
+          if (hh == 1) {   // both halves of M-tile i are out of TMEM: hand the accumulator slot back at once
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[c * kIrfRing + n % kIrfRing]);
+          }
+          // prefetch the next half (rows >= 561 of the last M-tile are padding: quadrants 2 and 3 skip it)
+          if (hh == 0) {
+            if (i * 128 + gw * 32 < kIrfPix) tmem_ld_32x16(lane_base + (c * kIrfRing + n % kIrfRing) * 32 + 16, r[1]);
+          } else if (i + 1 < kIrfMT) {
+            const int sl = c * kIrfRing + (n + 1) % kIrfRing;
+            IRF_T(tw0);
+            mbar_wait(&acc_full[sl], (uint32_t)(((n + 1) / kIrfRing) & 1));
+            IRF_T(tw1);
+            IRF_ACC(0, tw0, tw1);
+            IRF_ACC(1, tw1, tw0);  // (keeps the wait out of the epilogue time accumulated below)
+            tc_fence_after();
+            if ((i + 1) * 128 + gw * 32 < kIrfPix) tmem_ld_32x16(lane_base + sl * 32, r[0]);
+          }
+          if (pb < kIrfPix) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bj = bb[4 * hh + j];
               float4 o;
-              o.x = inside ? fmaxf(__uint_as_float(r[4 * j]) + bb.x, 0.f) : 0.f;
-              o.y = inside ? fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f) : 0.f;
-              o.z = inside ? fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f) : 0.f;
-              o.w = inside ? fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f) : 0.f;
-              dst[j ^ (pb & 7)] = o;  // 16-byte chunk swizzle: conflict-free stores here and loads below
+              o.x = fmaxf(__uint_as_float(r[hh][4 * j]) + bj.x, 0.f);
+              o.y = fmaxf(__uint_as_float(r[hh][4 * j + 1]) + bj.y, 0.f);
+              o.z = fmaxf(__uint_as_float(r[hh][4 * j + 2]) + bj.z, 0.f);
+              o.w = fmaxf(__uint_as_float(r[hh][4 * j + 3]) + bj.w, 0.f);
+              if (outside) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              // volatile: keeps this store after the prefetch of the next half in program order (ptxas otherwise
+              // sinks the TMEM load below the stores and its latency lands on the critical path)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 * hh + j) ^ sw) << 4)), "f"(o.x),
+                           "f"(o.y), "f"(o.z), "f"(o.w)
+                           : "memory");
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[slot]);
       }
+      IRF_T(t1);
+      IRF_ACC(1, t0b, t1);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the slab is complete
+      IRF_T(t2);
+      IRF_ACC(2, t1, t2);
       // ---- (2) depthwise 3x3 stride 2 + bd + ReLU -> (hi, lo) A tile of the project GEMM ----
-      mbar_wait(a2_empty, (uint32_t)((sc & 1) ^ 1));
       {
         const F4* w4 = reinterpret_cast<const F4*>(smem + kIrfOffDw) + c * 8 + cg;  // tap t at + t * 24
         const F4 bias4 = reinterpret_cast<const F4*>(smem + kIrfOffBd)[c * 8 + cg];
@@ -364,27 +449,27 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
           for (int kx = 0; kx < 3; ++kx) wk[ky][kx] = w4[(ky * 3 + kx) * (kIrfMid / 4)];
         uint8_t* ah = smem + kIrfOffA2;
         uint8_t* al = ah + 16384;
-#pragma unroll 1
+        IRF_T(t3);
+        mbar_wait(a2_empty, (uint32_t)((sc & 1) ^ 1));  // the previous slab's project MMAs have read the A tile
+        IRF_T(t4);
+        IRF_ACC(3, t3, t4);
+#pragma unroll
         for (int it = 0; it < 2; ++it) {
-          // 32 blocks of 2 x 2 output pixels: block id = it * 16 + gw * 4 + (lane >> 3)
-          const int blk = it * 16 + gw * 4 + (lane >> 3);
-          const int oy_l = (blk >> 3) * 2, ox_l = (blk & 7) * 2;
+          const int oy_l = oy_l0 + 4 * it;
+          const uint8_t* rows = slab + (2 * oy_l) * (kIrfIW * 128);
           F4 acc[2][2];
 #pragma unroll
           for (int y = 0; y < 2; ++y)
 #pragma unroll
             for (int x = 0; x < 2; ++x) acc[y][x] = bias4;
 #pragma unroll
-          for (int r = 0; r < 5; ++r) {
+          for (int rr = 0; rr < 5; ++rr) {
             F4 v[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const int pb = (2 * oy_l + r) * kIrfIW + 2 * ox_l + i;
-              v[i] = *reinterpret_cast<const F4*>(slab + pb * 128 + ((cg ^ (pb & 7)) << 4));
-            }
+            for (int i = 0; i < 5; ++i) v[i] = *reinterpret_cast<const F4*>(rows + rr * (kIrfIW * 128) + col_off[i]);
 #pragma unroll
             for (int y = 0; y < 2; ++y) {
-              const int ky = r - 2 * y;
+              const int ky = rr - 2 * y;
               if (ky >= 0 && ky < 3) {
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
@@ -421,20 +506,30 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(a2_full);
+      IRF_T(t5);
+      IRF_ACC(4, t2, t5);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // everyone has left the slab before it is rewritten
+      IRF_T(t6);
+      IRF_ACC(5, t5, t6);
     }
+#ifdef FEAR_IRF_TIMING
+    tacc[6] = clock64() - t_begin;
+    if (p.dbg && lane == 0)
+      for (int k = 0; k < 12; ++k) p.dbg[((long long)blockIdx.x * 8 + (warp - 8)) * 16 + k] = (unsigned long long)tacc[k];
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kIrfTmemCols);
   }
 }
 
 // X [B][H][W][16] -> Y [B][H/2][W/2][24].  Returns 0 on launch, 1 when the shape is not covered, < 0 on error.
-inline int launch_irf_s2(cudaStream_t s, const float* X, float* Y, const float* image, int B, int H, int W) {
+inline int launch_irf_s2(cudaStream_t s, const float* X, float* Y, const float* image, int B, int H, int W,
+                         unsigned long long* dbg = nullptr) {
   if (!available()) return 1;
   const int Ho = H / 2, Wo = W / 2;
   if (H % 2 || W % 2 || Ho % kIrfTH || Wo % kIrfTW) return 1;
@@ -446,6 +541,7 @@ inline int launch_irf_s2(cudaStream_t s, const float* X, float* Y, const float* 
   p.X = X;
   p.Y = Y;
   p.image = image;
+  p.dbg = dbg;
   p.B = B;
   p.H = H;
   p.W = W;

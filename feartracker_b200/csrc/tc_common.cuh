@@ -229,6 +229,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// Same, for single-thread producer / issuer roles that may wait long: back off between polls so the spinning
+// warp does not compete for issue slots with the warps that do the work on the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    __nanosleep(64);
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  __trap();
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

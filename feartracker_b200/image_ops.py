@@ -83,3 +83,68 @@ def rescale_bbox(bbox: Sequence[float], context: Sequence[float], instance_size:
     out = [round(bbox[0] * sx + context[0]), round(bbox[1] * sy + context[1]),
            max(3, round(bbox[2] * sx)), max(3, round(bbox[3] * sy))]
     return [int(v) for v in out]
+
+
+# ---------------------------------------------------------------------------------------------- device crop
+RESIZE_COEF_SCALE = np.float32(2048.0)  # cv::INTER_RESIZE_COEF_BITS = 11
+
+
+def _axis_table(src: int, dst: int, clamp: bool):
+    """Source offset + two fixed-point coefficients per destination index, as cv::resize (INTER_LINEAR, 8-bit)
+    computes them: float32 position (dst + 0.5) * scale - 0.5, floor, fraction; along x the offset is clamped into
+    the row and the fraction zeroed, along y only the ROW INDEX is clamped later (the kernel does that)."""
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * (float(src) / float(dst)) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp:
+        low, high = s < 0, s >= src - 1
+        f = np.where(low | high, np.float32(0.0), f)
+        s = np.where(low, 0, np.where(high, src - 1, s)).astype(np.int32)
+    a0 = np.rint((np.float32(1.0) - f) * RESIZE_COEF_SCALE).astype(np.int32)
+    a1 = np.rint(f * RESIZE_COEF_SCALE).astype(np.int32)
+    return s, a0, a1
+
+
+def resize_tables(src_w: int, src_h: int, dst: int) -> np.ndarray:
+    """(6 * dst,) int32: xofs, xa0, xa1, yofs, ya0, ya1 -- the tail of fear_crop_resize_u8's parameter block."""
+    return np.concatenate(_axis_table(src_w, dst, True) + _axis_table(src_h, dst, False)).astype(np.int32)
+
+
+def crop_params(bbox: Sequence[float], crop_size: int, offset: float, padding_value: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Parameter block of fear_crop_resize_u8 for the context crop around ``bbox`` plus the two values
+    ``extended_crop`` returns besides the image: the box inside the crop and the context box."""
+    ctx = context_box(bbox, offset)
+    cols, rows = int(ctx[2]), int(ctx[3])
+    box = trim_box([bbox[0] - ctx[0], bbox[1] - ctx[1], bbox[2], bbox[3]], (rows, cols))
+    if box[2] * box[3] == 0:
+        raise IndexError("target box has zero area inside its context crop")
+    pad = np.clip(np.rint(np.asarray(padding_value, dtype=np.float64)), 0, 255).astype(np.int32)  # cv::saturate_cast
+    head = np.array([ctx[0], ctx[1], cols, rows, pad[0], pad[1], pad[2], 0], dtype=np.int32)
+    params = np.concatenate([head, resize_tables(cols, rows, crop_size)])
+    x0, y0 = float(box[0]) / cols * crop_size, float(box[1]) / rows * crop_size
+    x1, y1 = float(box[0] + box[2]) / cols * crop_size, float(box[1] + box[3]) / rows * crop_size
+    return params, np.array([x0, y0, x1 - x0, y1 - y0]), ctx
+
+
+def crop_resize_reference(frame: np.ndarray, params: np.ndarray, crop_size: int) -> np.ndarray:
+    """numpy model of crop_resize_u8_kernel (same integer arithmetic); used by the CPU tests to pin the kernel's
+    formula to cv2.resize without a GPU."""
+    cx, cy, cw, ch = (int(v) for v in params[:4])
+    pad = params[4:7].astype(np.int64)
+    t = params[8:].reshape(6, crop_size).astype(np.int64)
+    xo, a0, a1, yo, b0, b1 = t
+    h, w = frame.shape[:2]
+
+    def px(ys, xs):
+        fy, fx = cy + ys[:, None], cx + xs[None, :]
+        inside = (fy >= 0) & (fy < h) & (fx >= 0) & (fx < w)
+        vals = frame[np.clip(fy, 0, h - 1), np.clip(fx, 0, w - 1)].astype(np.int64)
+        return np.where(inside[..., None], vals, pad[None, None, :])
+
+    x1 = np.minimum(xo + 1, cw - 1)
+    y0, y1 = np.clip(yo, 0, ch - 1), np.clip(yo + 1, 0, ch - 1)
+    s0 = px(y0, xo) * a0[None, :, None] + px(y0, x1) * a1[None, :, None]
+    s1 = px(y1, xo) * a0[None, :, None] + px(y1, x1) * a1[None, :, None]
+    out = (((b0[:, None, None] * (s0 >> 4)) >> 16) + ((b1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)

@@ -126,7 +126,79 @@ class FEARTracker(Tracker):
         return dict(bbox=pred_bbox)
 
     def _update_gpu_crop(self, image: np.ndarray) -> Dict[str, Any]:
-        raise NotImplementedError("gpu_crop: on-device crop + resize is not built in this library version")
+        """``gpu_crop=True``: the frame is uploaded once and the context crop + constant padding + bilinear resize of
+        get_extended_crop (reference utils/utils.py:215-253) runs on the device (fear_crop_resize_u8, bit-identical
+        to cv2's 8-bit fixed-point INTER_LINEAR) in the same CUDA graph as the network and the decode; the host only
+        computes the integer context box and the 2 x 256 resize coefficients."""
+        st, cfg = self.tracking_state, self.tracking_config
+        if cfg.get("smooth", False) or cfg.get("host_normalize", False) or image.shape[2] != 3:
+            raise NotImplementedError("gpu_crop covers the default uint8 RGB tracking path (no smooth / host_normalize)")
+        params, search_bbox, context = image_ops.crop_params(st.bbox, cfg["instance_size"], cfg["search_context"],
+                                                             st.mean_color)
+        st.mapping = context
+        st.prev_size = search_bbox[2:]
+        rec = self._track_record_gpu_crop(image, params)
+        pred_bbox = np.array([rec["x"], rec["y"], rec["w"], rec["h"]])
+        pred_bbox = image_ops.clamp_bbox(self._rescale_bbox(pred_bbox, context), image.shape)
+        st.bbox = pred_bbox
+        st.paths.append(pred_bbox)
+        return dict(bbox=pred_bbox)
+
+    def _track_record_gpu_crop(self, image: np.ndarray, params: np.ndarray):
+        from . import _lib
+
+        dev = self._device()
+        size = int(self.tracking_config["instance_size"])
+        h, w = image.shape[:2]
+        st = getattr(self, "_gpu_crop_state", None)
+        if st is None or st["device"] != dev or st["shape"] != (h, w) or st["params_pin"].numel() != params.size:
+            st = dict(device=dev, shape=(h, w), frame_pin=torch.empty((h, w, 3), dtype=torch.uint8).pin_memory(),
+                      frame=torch.empty((h, w, 3), dtype=torch.uint8, device=dev),
+                      params_pin=torch.empty(params.size, dtype=torch.int32).pin_memory(),
+                      params=torch.empty(params.size, dtype=torch.int32, device=dev),
+                      crop=torch.empty((1, size, size, 3), dtype=torch.uint8, device=dev),
+                      zf=torch.empty((1, 256, 8, 8), dtype=torch.float32, device=dev),
+                      box_pin=torch.empty((1, 48), dtype=torch.uint8).pin_memory(),
+                      graph=None, boxes=None, generation=None, zf_src=None, calls=0, graph_ok=True)
+            self._gpu_crop_state = st
+        np.copyto(st["frame_pin"].numpy(), image)
+        np.copyto(st["params_pin"].numpy(), params)
+        st["frame"].copy_(st["frame_pin"], non_blocking=True)
+        st["params"].copy_(st["params_pin"], non_blocking=True)
+        if st["zf_src"] is not self._template_features:
+            st["zf"].copy_(self._template_features)
+            st["zf_src"] = self._template_features
+        lib = _lib.load()
+
+        def step():
+            _lib.check(lib.fear_crop_resize_u8(st["frame"].data_ptr(), h, w, st["params"].data_ptr(), st["crop"].data_ptr(),
+                                               size, torch.cuda.current_stream(dev).cuda_stream), "fear_crop_resize_u8")
+            return self.net.track_boxes(st["crop"], st["zf"])
+
+        use_graph = self.tracking_config.get("cuda_graph", True) and st["graph_ok"]
+        if st["graph"] is not None and st["generation"] != self.net.generation():
+            st["graph"], st["calls"] = None, 0  # stale pointers (see _track_record)
+        if use_graph and st["graph"] is None and st["calls"] >= 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["boxes"] = step()
+                st["graph"], st["generation"] = g, self.net.generation()
+            except RuntimeError as exc:
+                import warnings
+
+                warnings.warn(f"FEARTracker: CUDA-graph capture of the gpu_crop step failed ({exc}); using eager launches")
+                st["graph_ok"] = False
+                torch.cuda.synchronize(dev)
+        if use_graph and st["graph"] is not None and st["graph_ok"]:
+            st["graph"].replay()
+            boxes = st["boxes"]
+        else:
+            boxes = step()
+        st["calls"] += 1
+        st["box_pin"].copy_(boxes, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return st["box_pin"].numpy().view(_lib.BOX_DTYPE).reshape(-1)[0].copy()
 
     def track(self, search_crop: np.ndarray) -> Tuple[np.ndarray, float]:
         if self.tracking_config.get("smooth", False):

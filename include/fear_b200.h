@@ -17,6 +17,7 @@
  *   fear_pack_weights     load_from_lighting + nn.Module.load_state_dict  utils/torch.py:11-24
  *
  *   fear_head_update      BoxTower.forward(search, kernel, update)   blocks.py:174-179
+ *   fear_crop_resize_u8   get_extended_crop (crop + pad + resize)    model_training/utils/utils.py:215-253
  *
  * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (torch keeps
  * ownership); tensors are dense fp32 in the reference's NCHW layout unless stated; `stream`
@@ -118,6 +119,17 @@ int fear_get_features_u8(FearContext* h, const uint8_t* d_img_u8, int B, int H, 
 /* template (B,3,128,128) + search (B,3,256,256) -> maps (+ boxes). */
 int fear_forward(FearContext* h, const float* d_template, const float* d_search, int B,
                  float* d_bbox, float* d_cls, FearBox* d_boxes, void* stream);
+
+/* Host pre-processing of the tracking loop on the device (get_extended_crop, reference
+ * model_training/utils/utils.py:215-253 = context crop, constant-colour padding, cv2.resize(INTER_LINEAR) on uint8):
+ * d_frame (H,W,3) uint8 RGB stays on the device; d_crop (out_size,out_size,3) uint8 is what fear_track_u8 /
+ * fear_get_features_u8 consume.  Bit-identical to OpenCV's 8-bit fixed-point bilinear kernel.  d_params (device,
+ * int32, 8 + 6 * out_size entries, so a captured CUDA graph sees per-frame values): [0..3] context x, y, w, h in frame
+ * coordinates (may leave the frame), [4..6] padding colour R, G, B, [7] 0, then xofs, xa0, xa1, yofs, ya0, ya1
+ * (out_size entries each): per-axis source offset and the two 11-bit coefficients, computed on the host exactly as
+ * cv::resize computes them (feartracker_b200.image_ops.resize_tables). */
+int fear_crop_resize_u8(const uint8_t* d_frame, int H, int W, const int32_t* d_params, uint8_t* d_crop, int out_size,
+                        void* stream);
 
 /* Decode maps produced elsewhere: bbox (B,4,16,16), cls logits (B,1,16,16) -> boxes[B].
  * apply_sigmoid = 0 treats cls as already-activated scores (decode(use_sigmoid=False)). */

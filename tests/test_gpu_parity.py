@@ -448,3 +448,40 @@ def test_reference_demo_flow_through_compat(net, tmp_path):
     assert proc.returncode == 0, proc.stderr[-2000:]
     line = [l for l in proc.stdout.splitlines() if l.startswith("BOXES ")][-1]
     assert json.loads(line[6:]) == golden("video_teacher.npz")["trajectory"][:8].tolist()
+
+
+def test_device_crop_resize_is_bit_identical_to_cv2(net):
+    """f1: fear_crop_resize_u8 (context crop + constant padding + 8-bit fixed-point bilinear resize on the device) ==
+    the host path (cv2.copyMakeBorder + cv2.resize), for windows inside and leaving the frame."""
+    from feartracker_b200 import image_ops
+
+    lib = _lib.init(0)
+    rng = np.random.default_rng(9)
+    frame = rng.integers(0, 256, (256, 480, 3), dtype=np.uint8)
+    mean = np.mean(frame, axis=(0, 1))
+    fd = torch.from_numpy(frame).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for box in ([163, 53, 45, 174], [0, 0, 30, 40], [450, 230, 30, 26], [-5, -7, 50, 60], [10, 200, 400, 56],
+                [177, 64, 128, 128]):
+        box = image_ops.clamp_bbox(box, frame.shape)
+        for size, off in ((256, 2), (128, 0.2), (256, 0.5)):
+            want = image_ops.extended_crop(frame, box, size, off, mean)[0]
+            params, _, _ = image_ops.crop_params(box, size, off, mean)
+            pd = torch.from_numpy(params).cuda()
+            out = torch.empty((size, size, 3), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.fear_crop_resize_u8(fd.data_ptr(), 256, 480, pd.data_ptr(), out.data_ptr(), size, st),
+                       "fear_crop_resize_u8")
+            assert np.array_equal(out.cpu().numpy(), want), (list(box), size, off)
+
+
+def test_gpu_crop_tracker_trajectory(net):
+    """f1 + C3: FEARTracker with gpu_crop=True (frame uploaded once; crop, resize, network and decode in one CUDA
+    graph) over the whole demo clip == the reference trajectory."""
+    g = golden("video_teacher.npz")
+    frames = fo.read_video_rgb(os.path.join(GOLDEN, "test.mp4"))
+    trk = fb.FEARTracker(net, cuda_id=0, gpu_crop=True, **fb.FEAR_XS_TRACKER_KWARGS)
+    trk.initialize(frames[0], g["init_bbox"])
+    traj = np.array([list(map(int, trk.update(f)["bbox"])) for f in frames[1:]], dtype=np.int64)
+    same = (traj == g["trajectory"]).all(1)
+    _dump("video_trajectory_gpu_crop.json", {"frames": int(len(traj)), "identical": int(same.sum())})
+    assert same.all(), int(np.argmin(same))

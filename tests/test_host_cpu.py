@@ -96,6 +96,27 @@ def test_smooth_postprocess_matches_reference():
         assert list(coords) == g["coords"][i].tolist() and np.array_equal(obox, g["box"][i])
 
 
+def test_device_crop_formula_matches_cv2_resize():
+    """f1: the integer arithmetic crop_resize_u8_kernel runs (numpy model image_ops.crop_resize_reference + the
+    host-computed coefficient tables) == copyMakeBorder + cv2.resize(INTER_LINEAR) of get_extended_crop, bit for bit,
+    including windows that leave the frame, up- and down-scaling and the 1:1 case."""
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, (256, 480, 3), dtype=np.uint8)
+    mean = np.mean(frame, axis=(0, 1))
+    boxes = [[163, 53, 45, 174], [0, 0, 30, 40], [450, 230, 30, 26], [200, 100, 3, 3], [-5, -7, 50, 60],
+             [10, 200, 400, 56], [100, 100, 64, 64], [300, 20, 17, 201], [177, 64, 128, 128]]
+    for box in boxes:
+        box = image_ops.clamp_bbox(box, frame.shape)
+        for size, off, pad in ((128, 0.2, None), (256, 2, mean), (256, 0.5, mean)):
+            want = image_ops.extended_crop(frame, box, size, off, pad)
+            params, inbox, ctx = image_ops.crop_params(box, size, off, mean if pad is None else pad)
+            assert params.dtype == np.int32 and params.size == 8 + 6 * size
+            got = image_ops.crop_resize_reference(frame, params, size)
+            assert np.array_equal(got, want[0]), (box, size, off)
+            np.testing.assert_allclose(inbox, want[1], rtol=0, atol=1e-12)
+            assert list(ctx) == list(want[2])
+
+
 def test_hydra_style_composer_and_reference_module_names(tmp_path):
     """f2: defaults list, ``# @package _global_``, ``${...}`` interpolation, overrides, ``_target_`` instantiate and
     the model_training.* / hydra / fire / imageio stand-ins (reference utils/hydra.py:33-39, demo_video.py:1-19)."""
