@@ -28,7 +28,6 @@ struct DwTmaParams {
 };
 
 constexpr int kDwCB = 32;           // channels per tile
-constexpr int kDwGroupWarps = 4;     // consumer warps working on one tile
 // GROUPS consumer groups per CTA; group g takes the tiles with (iteration % GROUPS) == g.  STAGES must be a
 // multiple of GROUPS: every stage then belongs to ONE group, which waits on / refills it strictly in order.
 // (With a shared ring a fast group could test full[s] while the previous use of that stage -- another group's
@@ -50,8 +49,11 @@ constexpr int dw_tma_smem_bytes() {
   return STAGES * DwTile<K, S, TH, TW>::kStageBytes + 2 * STAGES * 8 + 128;
 }
 
-template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, int GROUPS, bool RELU, bool BIAS>
-__global__ void __launch_bounds__(GROUPS * kDwGroupWarps * 32, 1)
+// GW = consumer warps working on one tile (per group).  Measured on B200 (round 2): 8 warps x (2 x 4)-pixel blocks
+// are 3 % SLOWER than 4 warps x (2 x 8)-pixel blocks -- the extra shared-memory loads per output cost more than the
+// extra resident warps hide, i.e. this kernel is bound by LDS / FFMA2 issue, not by latency.
+template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, int GROUPS, bool RELU, bool BIAS, int GW = 4>
+__global__ void __launch_bounds__(GROUPS * GW * 32, 1)
 dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
               const __grid_constant__ CUtensorMap tmBias, const DwTmaParams p) {
   using T = DwTile<K, S, TH, TW>;
@@ -74,7 +76,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kDwGroupWarps);
+      mbar_init(&empty[s], GW);
     }
     fence_mbar_init();
   }
@@ -105,7 +107,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
 
   // ---------------- consumers ----------------
   const int cg = lane & 7;  // channel group (float4) inside the 32-channel block
-  const int group = warp / kDwGroupWarps, gwarp = warp % kDwGroupWarps;
+  const int group = warp / GW, gwarp = warp % GW;
   int it = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
     if (it % GROUPS != group) continue;
@@ -124,7 +126,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const F4* b4p = reinterpret_cast<const F4*>(smem + s * T::kStageBytes + T::kInBytes + T::kWBytes);
 
 #pragma unroll 1
-    for (int pos = gwarp * 4 + (lane >> 3); pos < NPOS; pos += kDwGroupWarps * 4) {
+    for (int pos = gwarp * 4 + (lane >> 3); pos < NPOS; pos += GW * 4) {
       const int px = pos % PX, py = pos / PX;
       const int ox_l = px * TX, oy_l = py * TY;
       F4 acc[TY][TX];
@@ -195,13 +197,13 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
 }
 
 // Host launcher.  Returns 0 on launch, 1 when the shape is not covered (caller falls back), < 0 on error.
-template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, int GROUPS, bool RELU, bool BIAS>
+template <int K, int S, int TH, int TW, int TX, int TY, int STAGES, int GROUPS, bool RELU, bool BIAS, int GW = 4>
 inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, const float* bias, float* out, int B, int H,
                            int W, int C, int num_sms) {
   using T = DwTile<K, S, TH, TW>;
   const int Ho = H / S, Wo = W / S;
   if (Ho % TH || Wo % TW || C % 4) return 1;
-  auto kern = dw_tma_kernel<K, S, TH, TW, TX, TY, STAGES, GROUPS, RELU, BIAS>;
+  auto kern = dw_tma_kernel<K, S, TH, TW, TX, TY, STAGES, GROUPS, RELU, BIAS, GW>;
   constexpr int smem = dw_tma_smem_bytes<K, S, TH, TW, STAGES>();
   if (attr_needed(reinterpret_cast<const void*>(kern))) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
@@ -228,7 +230,7 @@ inline int launch_dw_tma_t(cudaStream_t s, const float* in, const float* w, cons
   p.num_tiles = B * p.tiles_x * p.tiles_y * p.cblocks;
   int grid = num_sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  if (launch_pdl(kern, dim3(grid), dim3(GROUPS * kDwGroupWarps * 32), (size_t)smem, s, tmIn, tmW, tmB, p) != cudaSuccess) return -31;
+  if (launch_pdl(kern, dim3(grid), dim3(GROUPS * GW * 32), (size_t)smem, s, tmIn, tmW, tmB, p) != cudaSuccess) return -31;
   return 0;
 }
 

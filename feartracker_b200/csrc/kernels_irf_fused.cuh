@@ -35,6 +35,8 @@
 // smem: A2 (hi, lo) 32 KB | weights image 40.25 KB (W1 [hi|lo] rows, W2 [hi;lo] x 3 chunks, dw, biases) | barriers |
 // 2 x 70.1 KB slabs = 214 KB.
 #pragma once
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace fear {
@@ -415,21 +417,29 @@ __global__ void __launch_bounds__(kIrfThreads, 1) irf_s2_fused_kernel(const IrfP
             if ((i + 1) * 128 + gw * 32 < kIrfPix) tmem_ld_32x16(lane_base + sl * 32, r[0]);
           }
           if (pb < kIrfPix) {
+            // (instruction diet: this loop is bound by the FMA / ALU issue rate, so the bias add is packed -- FADD2 --
+            // and the "pixel outside the image" select only runs for the few warps that hold such a pixel)
+            const bool any_outside = border && __any_sync(__activemask(), outside);
+            auto emit = [&](auto with_select) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 bj = bb[4 * hh + j];
-              float4 o;
-              o.x = fmaxf(__uint_as_float(r[hh][4 * j]) + bj.x, 0.f);
-              o.y = fmaxf(__uint_as_float(r[hh][4 * j + 1]) + bj.y, 0.f);
-              o.z = fmaxf(__uint_as_float(r[hh][4 * j + 2]) + bj.z, 0.f);
-              o.w = fmaxf(__uint_as_float(r[hh][4 * j + 3]) + bj.w, 0.f);
-              if (outside) o = make_float4(0.f, 0.f, 0.f, 0.f);
-              // volatile: keeps this store after the prefetch of the next half in program order (ptxas otherwise
-              // sinks the TMEM load below the stores and its latency lands on the critical path)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 * hh + j) ^ sw) << 4)), "f"(o.x),
-                           "f"(o.y), "f"(o.z), "f"(o.w)
-                           : "memory");
-            }
+              for (int j = 0; j < 4; ++j) {
+                const F4 bj = reinterpret_cast<const F4*>(bb)[4 * hh + j];
+                const unsigned long long s0 = fadd2(pack2(r[hh][4 * j], r[hh][4 * j + 1]), bj.lo);
+                const unsigned long long s1 = fadd2(pack2(r[hh][4 * j + 2], r[hh][4 * j + 3]), bj.hi);
+                float4 o;
+                o.x = fmaxf(__uint_as_float((uint32_t)s0), 0.f);
+                o.y = fmaxf(__uint_as_float((uint32_t)(s0 >> 32)), 0.f);
+                o.z = fmaxf(__uint_as_float((uint32_t)s1), 0.f);
+                o.w = fmaxf(__uint_as_float((uint32_t)(s1 >> 32)), 0.f);
+                if (decltype(with_select)::value && outside) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                // volatile: keeps this store after the prefetch of the next half in program order
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((4 * hh + j) ^ sw) << 4)), "f"(o.x),
+                             "f"(o.y), "f"(o.z), "f"(o.w)
+                             : "memory");
+              }
+            };
+            if (any_outside) emit(std::true_type{});
+            else emit(std::false_type{});
           }
         }
       }

@@ -298,6 +298,15 @@ struct __align__(16) F4 {
 __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
   asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
+// packed fp32 add (two independent round-to-nearest adds per issue slot; bit-identical to two __fadd_rn)
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
 __device__ __forceinline__ float4 f4_to_float4(const F4& v) {
   float4 r;
   r.x = __uint_as_float((unsigned)(v.lo & 0xffffffffull));
