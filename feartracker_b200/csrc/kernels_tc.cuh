@@ -331,15 +331,20 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
   const int S = p.stages;
-  uint8_t* ring = smem + p.w_region;
+  // DWK == 0: the lo halves of the A operand live in TWO dedicated 16 KB buffers, not in the TMA ring: a ring stage is
+  // then pure landing space (raw A tile + weight tiles), i.e. every byte of it can be "in flight" -- these GEMMs are
+  // bound by bytes in flight / loaded latency (Little's law: 3 x 44 KB per SM gave 22 B/clk), not by the tensor pipe.
+  uint8_t* lo_buf = smem + p.w_region;
+  uint8_t* ring = lo_buf + (DWK == 0 ? 2 * kCorrABytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S * p.stage_bytes);
   uint64_t* full = bars;
-  uint64_t* split = bars + S;
+  uint64_t* split = bars + S;  // DWK == 0: split[0..1] = lo buffer written; DWK > 0: per stage
   uint64_t* empty = bars + 2 * S;
   uint64_t* acc_full = bars + 3 * S;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* lo_empty = w_full + 1;  // [2] DWK == 0: the MMAs that read the lo buffer have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + 2);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;      // 8 warps x 2 buffers x 2 KB, 512-B aligned
   float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][256] per accumulator stage
 
@@ -369,6 +374,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&acc_empty[a], 8);
     }
     mbar_init(w_full, 1);
+    mbar_init(&lo_empty[0], 1);
+    mbar_init(&lo_empty[1], 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -379,10 +386,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   pdl_trigger();  // the next kernel may start its prologue on SMs we have left
   pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
 
+  constexpr int kAStage = DWK == 0 ? kCorrABytes : 2 * kCorrABytes;  // A part of a ring stage: raw tile (+ lo tile when fused)
   auto a_hi = [&](int s) { return ring + s * p.stage_bytes; };
-  auto a_lo = [&](int s) { return ring + s * p.stage_bytes + kCorrABytes; };
-  auto w_hi = [&](int s) { return resident_w ? smem : ring + s * p.stage_bytes + 2 * kCorrABytes; };
-  auto w_lo = [&](int s) { return resident_w ? smem + w_bytes : ring + s * p.stage_bytes + 2 * kCorrABytes + w_bytes; };
+  auto a_lo = [&](int s) { return ring + s * p.stage_bytes + kCorrABytes; };  // (DWK > 0 only)
+  auto w_hi = [&](int s) { return resident_w ? smem : ring + s * p.stage_bytes + kAStage; };
+  auto w_lo = [&](int s) { return resident_w ? smem + w_bytes : ring + s * p.stage_bytes + kAStage + w_bytes; };
   // fused-depthwise stages: [a_hi][a_lo][w_hi][w_lo][input box][dw weights DWK*DWK x 32][dw bias 32]
   auto dw_box = [&](int s) { return ring + s * p.stage_bytes + 2 * kCorrABytes + 2 * w_bytes; };
   auto dw_wts = [&](int s) { return dw_box(s) + p.box_bytes; };
@@ -432,17 +440,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, p.NT);
       const uint32_t idesc2 = umma_idesc_tf32(128, 2 * p.NT);  // stacked [W_hi ; W_lo] (NT <= 128)
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, q = 0;
       uint32_t phase = 0, acc_phase = 0;
       if (resident_w) mbar_wait(w_full, 0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * p.acc_stride;  // main; + NT = correction accumulator (split_acc)
-        for (int c = 0; c < p.num_chunks; ++c) {
-          mbar_wait(&split[stage], phase);
+        for (int c = 0; c < p.num_chunks; ++c, ++q) {
+          if constexpr (DWK == 0) mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> stage landed)
+          else mbar_wait(&split[stage], phase);
           tc_fence_after();
-          const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(stage));
+          const uint32_t ah = smem_u32(a_hi(stage));
+          const uint32_t al = DWK == 0 ? smem_u32(lo_buf + (q & 1) * kCorrABytes) : smem_u32(a_lo(stage));
           const uint32_t bh = smem_u32(w_hi(stage)), bl = smem_u32(w_lo(stage));
           const int ksteps = (c == p.num_chunks - 1) ? p.last_ksteps : 4;  // K tail: skip all-zero K-steps
           for (int j = 0; j < ksteps; ++j) {
@@ -462,6 +472,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           tc_commit(&empty[stage]);
+          if constexpr (DWK == 0) tc_commit(&lo_empty[q & 1]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -555,12 +566,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
-    } else
+    } else {
+    int q = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int c = 0; c < p.num_chunks; ++c) {
+      for (int c = 0; c < p.num_chunks; ++c, ++q) {
         mbar_wait(&full[stage], phase);
+        mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
-        float4* al = reinterpret_cast<float4*>(a_lo(stage));
+        float4* al = reinterpret_cast<float4*>(lo_buf + (q & 1) * kCorrABytes);
 #pragma unroll
         for (int i = 0; i < kCorrABytes / 16 / 256; ++i) {
           const float4 v = ah[ts + i * 256];  // the raw tile is the hi operand as it stands (hardware truncation)
@@ -573,12 +586,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&split[stage]);
+        if (lane == 0) mbar_arrive(&split[q & 1]);
         if (++stage == S) {
           stage = 0;
           phase ^= 1;
         }
       }
+    }
     }
   } else {
     // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
@@ -806,9 +820,9 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.dw_relu = p.dw_bias = p.box_bytes = 0;
   const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1;
   p.w_region = resident ? 2 * p.NT * 128 : 0;
-  p.stage_bytes = resident ? 2 * kCorrABytes : 2 * kCorrABytes + 2 * p.NT * 128;
-  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region) / p.stage_bytes;
-  if (p.stages > (resident ? 5 : 6)) p.stages = resident ? 5 : 6;
+  p.stage_bytes = resident ? kCorrABytes : kCorrABytes + 2 * p.NT * 128;  // landing space only (lo tiles: 2 extra buffers)
+  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region - 2 * kCorrABytes) / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -22;
   int cols = 32;
   while (cols < 2 * p.acc_stride) cols <<= 1;
@@ -825,7 +839,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   CUtensorMap tmC;  // output: [M][N] window of C (pitch ldc); 32 x 16 boxes, SWIZZLE_64B staging; clips the tails
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
-  const int smem_bytes = p.w_region + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
+  const int smem_bytes = p.w_region + 2 * kCorrABytes + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
   if (launch_pdl(pw_tc_kernel<0>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA, tmA, p) !=
       cudaSuccess)
     return -23;
