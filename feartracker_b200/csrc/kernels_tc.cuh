@@ -310,7 +310,8 @@ struct PwParams {
   int acc_stride; // TMEM columns per accumulator stage: 2*NT (main + correction) or NT
   // --- fused depthwise producer (pw_tc_kernel<DWK>, DWK = 3 | 5): the A operand is dw(X) computed on the fly ---
   int dw_relu, dw_bias;  // ReLU / bias of the depthwise stage
-  int box_bytes;         // bytes of one (8 + DWK - 1) x (16 + DWK - 1) x 32-channel input box
+  int box_bytes;         // bytes of one (tile rows + DWK - 1) x (map width + DWK - 1) x 32-channel input box
+  int map_w;             // fused depthwise: square map side, 16 (tile = 8 rows x 16) or 32 (tile = 4 rows x 32)
   int w_region;   // > 0: the (hi, lo) weight tile is loaded ONCE into the first w_region bytes of smem (layers with one
                   // N tile and one K chunk) and the ring stages hold activations only
 };
@@ -323,7 +324,7 @@ constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue war
 // groups of four "split" warps take alternate chunks, run the depthwise conv out of shared memory (same FMA order as
 // dw_tma_kernel => same fp32 values as the unfused pair of kernels) and write the (hi, lo) A tiles directly in the
 // SWIZZLE_128B K-major layout the MMA descriptors expect.  Everything downstream is unchanged.
-template <int DWK>
+template <int DWK, int MW = 16>
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC,
@@ -410,9 +411,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           if constexpr (DWK > 0) {
-            // 16x16 maps: tile mt = rows [8*(mt&1), +8) of frame mt>>1; the box carries a DWK/2 halo on every side
+            // tile mt = 128 / map_w consecutive rows of one frame (8 rows of a 16x16 map, 4 rows of a 32x32 map); the box
+            // carries a DWK/2 halo on every side (zero-filled by TMA outside the map = the conv padding)
+            constexpr int th = 128 / MW, tpf = MW / th;
             mbar_arrive_expect_tx(&full[stage], p.box_bytes + DWK * DWK * 128 + (p.dw_bias ? 128 : 0) + 2 * w_bytes);
-            tma_load_4d(dw_box(stage), &tmA, &full[stage], c * 32, -(DWK / 2), (mt & 1) * 8 - DWK / 2, mt >> 1);
+            tma_load_4d(dw_box(stage), &tmA, &full[stage], c * 32, -(DWK / 2), (mt % tpf) * th - DWK / 2, mt / tpf);
             tma_load_2d(dw_wts(stage), &tmDW, &full[stage], c * 32, 0);
             if (p.dw_bias) tma_load_2d(dw_bia(stage), &tmDB, &full[stage], c * 32, 0);
             tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
@@ -489,10 +492,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t phase = 0;
     if constexpr (DWK > 0) {
       // ---- fused depthwise: group g (4 warps) owns stage g (S == 2); thread = (4-channel group, 2 x 4 pixel block) ----
-      constexpr int K = DWK, IW = 16 + K - 1, TX = 4, TY = 2, NIN = TX + K - 1, NR = TY + K - 1;
+      constexpr int K = DWK, TX = 4, TY = 2, NIN = TX + K - 1, NR = TY + K - 1;
+      constexpr int IW = MW + K - 1, PXN = MW / TX;  // 16 positions: 4 across x 4 down (16x16) | 8 x 2 (32x32)
       const int group = (warp - 2) >> 2, gw = (warp - 2) & 3;
-      const int cg = lane & 7, pos = gw * 4 + (lane >> 3);  // 16 positions: 4 across x 4 down
-      const int x0 = (pos & 3) * TX, r0 = (pos >> 2) * TY;
+      const int cg = lane & 7, pos = gw * 4 + (lane >> 3);
+      const int x0 = (pos % PXN) * TX, r0 = (pos / PXN) * TY;
       int chunk = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int c = 0; c < p.num_chunks; ++c, ++chunk) {
@@ -551,7 +555,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 split_tf32_trunc(v.y, h.y, l.y);
                 split_tf32_trunc(v.z, h.z, l.z);
                 split_tf32_trunc(v.w, h.w, l.w);
-                const int R = (r0 + y) * 16 + x0 + i;                         // A-tile row = pixel inside the 8 x 16 tile
+                const int R = (r0 + y) * MW + x0 + i;                         // A-tile row = pixel inside the tile
                 const int off = R * 128 + ((cg ^ (R & 7)) << 4);              // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
                 *reinterpret_cast<float4*>(ah + off) = v;                     // raw fp32 = hi operand (hardware truncation)
                 *reinterpret_cast<float4*>(al + off) = l;
@@ -790,7 +794,9 @@ inline bool pw_supported(int cin, int cout) {
 inline int init_pw() {
   if (cudaFuncSetAttribute(pw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(pw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
+      cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<5, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
@@ -818,6 +824,7 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
   p.dw_relu = p.dw_bias = p.box_bytes = 0;
+  p.map_w = 16;
   const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1;
   p.w_region = resident ? 2 * p.NT * 128 : 0;
   p.stage_bytes = resident ? kCorrABytes : kCorrABytes + 2 * p.NT * 128;  // landing space only (lo tiles: 2 extra buffers)
@@ -851,11 +858,12 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
 // Returns 1 when the shape is not covered (caller runs the two kernels separately).
 inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const float* dw_w, const float* dw_b, int dw_relu,
                         const float* w_hi, const float* w_lo, const float* bias, const float* R, int ldr, float* C,
-                        int ldc, int N, int K, int relu) {
+                        int ldc, int N, int K, int relu, int map_w = 16) {
   if (!available()) return -20;
-  if ((dw_k != 3 && dw_k != 5) || K % 4) return 1;
+  if ((dw_k != 3 && dw_k != 5) || K % 4 || (map_w != 16 && map_w != 32)) return 1;
   PwParams p;
-  const int M = B * 256;
+  const int M = B * map_w * map_w;
+  p.map_w = map_w;
   p.bias = bias;
   p.R = R;
   p.C = C;
@@ -873,7 +881,7 @@ inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const f
   p.relu = relu;
   p.dw_relu = dw_relu;
   p.dw_bias = dw_b != nullptr;
-  const int ih = 8 + dw_k - 1, iw = 16 + dw_k - 1;
+  const int ih = 128 / map_w + dw_k - 1, iw = map_w + dw_k - 1;
   p.box_bytes = ih * iw * 128;
   p.w_region = 0;
   p.stage_bytes = (2 * kCorrABytes + 2 * p.NT * 128 + p.box_bytes + dw_k * dw_k * 128 + 128 + 1023) & ~1023;
@@ -883,7 +891,7 @@ inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const f
   while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap tmX, tmWh, tmWl, tmC, tmDW, tmDB;
-  int r = make_tmap_nhwc(&tmX, X, (uint64_t)B, 16, 16, (uint64_t)K, 32, iw, ih);
+  int r = make_tmap_nhwc(&tmX, X, (uint64_t)B, (uint64_t)map_w, (uint64_t)map_w, (uint64_t)K, 32, iw, ih);
   if (r) return r;
   r = make_tmap_2d(&tmWh, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, p.NT, 32);
   if (r) return r;
@@ -902,10 +910,13 @@ inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const f
   const int tiles = (M / 128) * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const size_t smem_bytes = (size_t)2 * p.stage_bytes + 1024 + kPwTailBytes;
-  cudaError_t e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC,
-                                         tmDW, tmDB, p)
-                            : launch_pdl(pw_tc_kernel<3>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC,
-                                         tmDW, tmDB, p);
+  cudaError_t e;
+  if (map_w == 16)
+    e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5, 16>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC, tmDW, tmDB, p)
+                  : launch_pdl(pw_tc_kernel<3, 16>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC, tmDW, tmDB, p);
+  else
+    e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5, 32>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC, tmDW, tmDB, p)
+                  : launch_pdl(pw_tc_kernel<3, 32>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC, tmDW, tmDB, p);
   return e == cudaSuccess ? 0 : -23;
 }
 

@@ -261,10 +261,10 @@ def test_fused_stem_block_is_bit_identical(net):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("mask", ["0", "1", "2"])
+@pytest.mark.parametrize("mask", ["0", "1", "2", "3"])
 def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
     """fuse_dwpw: depthwise + 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK>) -- bit 0: the 16x16-stage backbone blocks,
-    bit 1: the head's SepConvs; default 3 = both.  The depthwise values are computed in the same order as
+    bit 2: also the 32x32-stage blocks, bit 1: the head's SepConvs; default 7 = all.  The depthwise values are computed in the same order as
     dw_tma_kernel and the GEMM is the same MMA sequence, so switching either fusion off may not change a bit."""
     zt, xt, _, _ = fo.synthetic_crops(3)
     zf = net.get_features(zt.cuda())
@@ -275,7 +275,7 @@ def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
         got_f = net.get_features(xt.cuda())
         got = net.track(xt.cuda(), zf)
     finally:
-        net.set_option("fuse_dwpw", "3")
+        net.set_option("fuse_dwpw", "7")
     assert torch.equal(ref_f, got_f), float((ref_f - got_f).abs().max())
     assert torch.equal(ref[R], got[R]) and torch.equal(ref[C], got[C])
 
