@@ -345,7 +345,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint64_t* lo_empty = w_full + 1;  // [2] DWK == 0: the MMAs that read the lo buffer have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + 2);
+  uint64_t* wfl = lo_empty + 2;     // [2] DWK > 0: the stage's weight tiles have landed (TMA producer warp)
+  uint64_t* box_empty = wfl + 2;    // [2] DWK > 0: the 4 depthwise warps of the owning group have read the input box
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(box_empty + 2);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 1024;      // 8 warps x 2 buffers x 2 KB, 512-B aligned
   float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][256] per accumulator stage
 
@@ -377,6 +379,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_init(w_full, 1);
     mbar_init(&lo_empty[0], 1);
     mbar_init(&lo_empty[1], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&wfl[a], 1);
+      mbar_init(&box_empty[a], 4);
+    }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -411,15 +417,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int c = 0; c < p.num_chunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           if constexpr (DWK > 0) {
-            // tile mt = 128 / map_w consecutive rows of one frame (8 rows of a 16x16 map, 4 rows of a 32x32 map); the box
-            // carries a DWK/2 halo on every side (zero-filled by TMA outside the map = the conv padding)
-            constexpr int th = 128 / MW, tpf = MW / th;
-            mbar_arrive_expect_tx(&full[stage], p.box_bytes + DWK * DWK * 128 + (p.dw_bias ? 128 : 0) + 2 * w_bytes);
-            tma_load_4d(dw_box(stage), &tmA, &full[stage], c * 32, -(DWK / 2), (mt % tpf) * th - DWK / 2, mt / tpf);
-            tma_load_2d(dw_wts(stage), &tmDW, &full[stage], c * 32, 0);
-            if (p.dw_bias) tma_load_2d(dw_bia(stage), &tmDB, &full[stage], c * 32, 0);
-            tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
-            tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
+            // weight tiles only: the input box of a stage is re-filled by the depthwise group that owns the stage as soon
+            // as it has read it (well before the MMAs release the stage), see below
+            mbar_arrive_expect_tx(&wfl[stage], 2 * w_bytes);
+            tma_load_2d(w_hi(stage), &tmWh, &wfl[stage], c * 32, nt * p.NT);
+            tma_load_2d(w_lo(stage), &tmWl, &wfl[stage], c * 32, nt * p.NT);
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
@@ -451,8 +453,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t d = tmem_base + acc * p.acc_stride;  // main; + NT = correction accumulator (split_acc)
         for (int c = 0; c < p.num_chunks; ++c, ++q) {
-          if constexpr (DWK == 0) mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> stage landed)
-          else mbar_wait(&split[stage], phase);
+          if constexpr (DWK == 0) {
+            mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> stage landed)
+          } else {
+            mbar_wait(&split[stage], phase);  // depthwise output (hi, lo) written
+            mbar_wait(&wfl[stage], phase);    // weight tiles landed
+          }
           tc_fence_after();
           const uint32_t ah = smem_u32(a_hi(stage));
           const uint32_t al = DWK == 0 ? smem_u32(lo_buf + (q & 1) * kCorrABytes) : smem_u32(a_lo(stage));
@@ -497,6 +503,24 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int group = (warp - 2) >> 2, gw = (warp - 2) & 3;
       const int cg = lane & 7, pos = gw * 4 + (lane >> 3);
       const int x0 = (pos % PXN) * TX, r0 = (pos / PXN) * TY;
+      // The group's leader thread issues the TMA of the group's NEXT input box (chunk + 2, same stage) as soon as all
+      // four warps have read the current one -- not when the MMAs release the stage: the box is ~1/3 of a stage and its
+      // load latency (~2 us under load) was fully exposed with two stages.
+      auto issue_box = [&](int t2, int c2) {
+        while (c2 >= p.num_chunks) {
+          c2 -= p.num_chunks;
+          t2 += gridDim.x;
+        }
+        if (t2 >= num_tiles) return;
+        constexpr int th = 128 / MW, tpf = MW / th;
+        const int mt2 = t2 / p.num_n_tiles, st = group;  // S == 2: stage = chunk & 1 = group
+        mbar_arrive_expect_tx(&full[st], p.box_bytes + DWK * DWK * 128 + (p.dw_bias ? 128 : 0));
+        tma_load_4d(dw_box(st), &tmA, &full[st], c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
+        tma_load_2d(dw_wts(st), &tmDW, &full[st], c2 * 32, 0);
+        if (p.dw_bias) tma_load_2d(dw_bia(st), &tmDB, &full[st], c2 * 32, 0);
+      };
+      const bool leader = gw == 0 && lane == 0;
+      if (leader) issue_box(blockIdx.x, group);  // the group's first chunk
       int chunk = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int c = 0; c < p.num_chunks; ++c, ++chunk) {
@@ -537,6 +561,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
               }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&box_empty[stage]);  // this warp has read the box
+            if (leader) {
+              mbar_wait(&box_empty[stage], phase);
+              issue_box(t, c + 2);
+            }
+            mbar_wait(&empty[stage], phase ^ 1);  // the MMAs of this stage's previous chunk have read its A tiles
             uint8_t* ah = a_hi(stage);
             uint8_t* al = a_lo(stage);
 #pragma unroll
