@@ -32,12 +32,17 @@
 namespace fear {
 namespace tc {
 
-constexpr int kCorrStages = 4;
+constexpr int kCorrStages = 6;
 constexpr int kCorrChunk = 32;                 // channels per stage = one 128-byte swizzled row
 constexpr int kCorrABytes = 128 * 128;         // [128 pixels][32 ch] fp32
 constexpr int kCorrBBytes = 64 * 128;          // [64 template cells][32 ch] fp32
-constexpr int kCorrStageBytes = 2 * (kCorrABytes + kCorrBBytes);
-constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
+// A ring stage is pure TMA landing space (raw x tile + raw z tile, 24 KB); the lo halves of both operands go to two
+// dedicated buffers.  With (hi, lo) pairs inside the stages (round 1: 4 x 48 KB) only 96 KB per SM could be in flight
+// and the kernel sat at 64-67 % of the HBM roofline; 6 x 24 KB in the same shared-memory budget keep 144 KB in flight.
+constexpr int kCorrStageBytes = kCorrABytes + kCorrBBytes;
+constexpr int kCorrLoBytes = kCorrABytes + kCorrBBytes;
+constexpr int kCorrSmemBytes =
+    kCorrStages * kCorrStageBytes + 2 * kCorrLoBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
 constexpr int kCorrThreads = 448;  // producer, MMA, 8 split warps, 4 epilogue warps
 constexpr int kCorrSplitThreads = 256;
 constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) columns
@@ -47,14 +52,16 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                float* __restrict__ cat, int num_frames, int z_mod) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes);
+  uint8_t* lo_buf = smem + kCorrStages * kCorrStageBytes;  // [2][x_lo 16 KB | z_lo 8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_buf + 2 * kCorrLoBytes);
   uint64_t* full = bars;                       // [stages] TMA landed
-  uint64_t* split = bars + kCorrStages;        // [stages] hi/lo tiles ready for the tensor core
-  uint64_t* empty = bars + 2 * kCorrStages;    // [stages] MMAs reading the stage have completed
-  uint64_t* acc_full = bars + 3 * kCorrStages; // [2] accumulator complete
+  uint64_t* empty = bars + kCorrStages;        // [stages] MMAs reading the stage have completed
+  uint64_t* split = bars + 2 * kCorrStages;    // [2] lo buffer written
+  uint64_t* lo_empty = split + 2;              // [2] MMAs reading the lo buffer have completed
+  uint64_t* acc_full = lo_empty + 2;           // [2] accumulator complete
   uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB (20 mbarriers + the TMEM slot < 256 B)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = num_frames * 2;
@@ -70,10 +77,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 64) {
     for (int s = 0; s < kCorrStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], kCorrSplitThreads / 32);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&split[a], kCorrSplitThreads / 32);
+      mbar_init(&lo_empty[a], 1);
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], 4);
     }
@@ -87,9 +95,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   auto a_hi = [&](int s) { return smem + s * kCorrStageBytes; };
-  auto a_lo = [&](int s) { return smem + s * kCorrStageBytes + kCorrABytes; };
-  auto b_hi = [&](int s) { return smem + s * kCorrStageBytes + 2 * kCorrABytes; };
-  auto b_lo = [&](int s) { return smem + s * kCorrStageBytes + 2 * kCorrABytes + kCorrBBytes; };
+  auto b_hi = [&](int s) { return smem + s * kCorrStageBytes + kCorrABytes; };
+  auto a_lo = [&](int q) { return lo_buf + (q & 1) * kCorrLoBytes; };
+  auto b_lo = [&](int q) { return lo_buf + (q & 1) * kCorrLoBytes + kCorrABytes; };
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -116,30 +124,29 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
-      constexpr uint32_t idesc2 = umma_idesc_tf32(128, 128);  // B' = [z_hi ; z_lo] stacked: 128 rows
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, q = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * 128;  // main accumulator; +64 = correction accumulator
-        for (int c = 0; c < 256 / kCorrChunk; ++c) {
-          mbar_wait(&split[stage], phase);
+        for (int c = 0; c < 256 / kCorrChunk; ++c, ++q) {
+          mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> the stage has landed)
           tc_fence_after();
-          const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(stage));
-          const uint32_t bh = smem_u32(b_hi(stage)), bl = smem_u32(b_lo(stage));
+          const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(q));
+          const uint32_t bh = smem_u32(b_hi(stage)), bl = smem_u32(b_lo(q));
 #pragma unroll
           for (int j = 0; j < 4; ++j) {  // 4 K-steps of 8 tf32 (32 B) inside the 128-B swizzle row
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
             // so the (truncating) tensor-core adder rounds the big sum 3x less often
-            // the hi and lo template tiles are adjacent in smem, so ONE N=128 MMA yields [x_hi*z_hi | x_hi*z_lo]
-            // in the adjacent (main | correction) accumulators and x_hi is read from smem once, not twice
-            mma_tf32_ss(d, dah, dbh, idesc2, (c | j) != 0);
-            mma_tf32_ss(d + 64, dal, dbh, idesc, 1);
+            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);       // main += x_hi z_hi
+            mma_tf32_ss(d + 64, dah, dbl, idesc, (c | j) != 0);  // corr += x_hi z_lo
+            mma_tf32_ss(d + 64, dal, dbh, idesc, 1);             // corr += x_lo z_hi
           }
           tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+          tc_commit(&lo_empty[q & 1]);
           if (++stage == kCorrStages) {
             stage = 0;
             phase ^= 1;
@@ -153,13 +160,14 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp < 2 + kCorrSplitThreads / 32) {
     // ===================================== operand split ====================================
     const int ts = threadIdx.x - 64;  // 0..255
-    int stage = 0;
+    int stage = 0, q = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int c = 0; c < 256 / kCorrChunk; ++c) {
+      for (int c = 0; c < 256 / kCorrChunk; ++c, ++q) {
         mbar_wait(&full[stage], phase);
+        mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
-        float4* al = reinterpret_cast<float4*>(a_lo(stage));
+        float4* al = reinterpret_cast<float4*>(a_lo(q));
         {
 #pragma unroll
           for (int i = 0; i < kCorrABytes / 16 / kCorrSplitThreads; ++i) {
@@ -174,7 +182,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             al[ts + i * kCorrSplitThreads] = l;
           }
           float4* bh = reinterpret_cast<float4*>(b_hi(stage));
-          float4* bl = reinterpret_cast<float4*>(b_lo(stage));
+          float4* bl = reinterpret_cast<float4*>(b_lo(q));
 #pragma unroll
           for (int i = 0; i < kCorrBBytes / 16 / kCorrSplitThreads; ++i) {
             const float4 v = bh[ts + i * kCorrSplitThreads];
@@ -188,7 +196,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&split[stage]);
+        if (lane == 0) mbar_arrive(&split[q & 1]);
         if (++stage == kCorrStages) {
           stage = 0;
           phase ^= 1;
