@@ -481,7 +481,7 @@ def main():
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         roofline = {
-            "kernel": "tc::corr_tc_kernel -- pixel-wise correlation, both head branches in one launch", "bound": "hbm",
+            "kernel": "tc::corr_ts_kernel -- pixel-wise correlation, both head branches in one launch", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
             "algorithmic_bytes_per_launch": int(bytes_per_launch),

@@ -1156,6 +1156,15 @@ extern "C" int fear_debug_irf_timing(FearContext* c, unsigned long long* host_ou
 }
 #endif
 
+#ifdef FEAR_CORR_ABLATE
+// Profiling build only (FEAR_NVCC_FLAGS=-DFEAR_CORR_ABLATE; not in the public header): roles of corr_ts_kernel that skip
+// their work.  1 = MMAs, 2 = convert, 4 = epilogue, 8 = x tiles re-read from L2 (no HBM stream).  Results are garbage.
+extern "C" int fear_debug_corr_ablate(int mask) {
+  CUDA_TRY(cudaMemcpyToSymbol(tc::g_corr_ablate, &mask, sizeof(int)));
+  return 0;
+}
+#endif
+
 extern "C" int64_t fear_launch_count(const FearContext* c) { return c ? c->launches : 0; }
 extern "C" int64_t fear_generation(const FearContext* c) { return c ? c->generation : -1; }
 

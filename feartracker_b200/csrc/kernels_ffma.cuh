@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(256) crop_resize_u8_kernel(const uint8_t* __re
 // Pixel-wise correlation straight on the reference's layouts (MobileCorrelation.forward, blocks.py:121-123):
 //   out[b, 256 + k, p] = sum_c z[b, c, k] * x[b, c, p],  z (Bz,256,64), x (B,256,256), out (B,320,256).
 // Compatibility kernel of the workspace-free C entry point fear_corr_concat_f32; the hot path runs
-// tc::corr_tc_kernel on the channels-last concat buffer instead.  grid (4, B), 256 threads: 64 pixels x 4 groups
+// tc::corr_ts_kernel on the channels-last concat buffer instead.  grid (4, B), 256 threads: 64 pixels x 4 groups
 // of 16 template cells, the template streamed through shared memory in 64-channel slices.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) corr_nchw_ffma_kernel(const float* __restrict__ z, long long z_stride,

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA kernels of the FEAR-XS hot path (sm_100a only).
 //
-// corr_tc_kernel -- the pixel-wise template (x) search correlation (MobileCorrelation.forward's matmul,
+// corr_ts_kernel -- the pixel-wise template (x) search correlation (MobileCorrelation.forward's matmul,
 // reference model_training/model/blocks.py:123) on the 5th-generation tensor cores:
 //
 //     s[b, p, k] = sum_c x[b, p, c] * z[b, k, c]        p in 256 search cells, k in 64 template cells, c in 256
@@ -11,18 +11,11 @@
 // reference costs nothing and the kernel moves exactly the algorithmic bytes (z + x in, s out).
 //
 // fp32 fidelity: kind::tf32 keeps 11 significand bits, which fails the 1e-3 parity bar (SURVEY.md
-// section 7.4), so each operand is split on the fly into tf32 (hi, lo) pairs and three MMAs
-// (hi*hi + lo*hi + hi*lo) accumulate in TMEM in fp32 -- error ~1e-6, still far above the FFMA rate.
+// section 7.4), so each operand is split on the fly into tf32 (hi, lo) pairs and three products
+// (hi*hi + hi*lo + lo*hi) accumulate in TMEM in fp32 -- error ~1e-6, still far above the FFMA rate.
 //
-// Structure (persistent, one CTA per SM, warp-specialised, mbarrier pipelines):
-//   warp 0      TMA producer: per 32-channel chunk, x tile [128 p][32 c] + z tile [64 k][32 c] -> smem
-//   warp 1      TMEM owner + MMA issuer: 4 K-steps x 3 MMAs (128x64x8) per chunk, tcgen05.commit
-//   warps 2-5   operand split: raw fp32 tile -> tf32 hi (in place) and lo (second tile), same swizzled
-//               positions, then fence.proxy.async so the tensor core sees the generic-proxy writes
-//   warps 6-9   epilogue: tcgen05.ld 128x64 fp32 accumulator -> registers -> global (256 B per pixel)
-// Two TMEM accumulator sets (2 x (64 main + 64 correction) columns) let the epilogue of tile t overlap
-// the MMAs of tile t+1;
-// a 4-stage smem ring (4 x 48 KB) keeps ~96 KB of loads in flight per SM.
+// pw_tc_kernel -- every 1x1 convolution as a 3xTF32 GEMM on the same pipeline (optionally with the preceding
+// depthwise conv computed by its producer warps).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -32,57 +25,84 @@
 namespace fear {
 namespace tc {
 
-constexpr int kCorrStages = 6;
 constexpr int kCorrChunk = 32;                 // channels per stage = one 128-byte swizzled row
 constexpr int kCorrABytes = 128 * 128;         // [128 pixels][32 ch] fp32
 constexpr int kCorrBBytes = 64 * 128;          // [64 template cells][32 ch] fp32
-// A ring stage is pure TMA landing space (raw x tile + raw z tile, 24 KB); the lo halves of both operands go to two
-// dedicated buffers.  With (hi, lo) pairs inside the stages (round 1: 4 x 48 KB) only 96 KB per SM could be in flight
-// and the kernel sat at 64-67 % of the HBM roofline; 6 x 24 KB in the same shared-memory budget keep 144 KB in flight.
-constexpr int kCorrStageBytes = kCorrABytes + kCorrBBytes;
-constexpr int kCorrLoBytes = kCorrABytes + kCorrBBytes;
-constexpr int kCorrSmemBytes =
-    kCorrStages * kCorrStageBytes + 2 * kCorrLoBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
-constexpr int kCorrThreads = 448;  // producer, MMA, 8 split warps, 4 epilogue warps
-constexpr int kCorrSplitThreads = 256;
-constexpr int kCorrTmemCols = 256;  // 2 buffers x (main 64 + correction 64) columns
 
-__global__ void __launch_bounds__(kCorrThreads, 1)
-corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+// ------------------------------------------------------------------------------------------
+// corr_ts_kernel -- the same correlation with the search-feature operand in TENSOR MEMORY ("TS" form) and TWO MMA issuers.
+//
+// Two measured facts shape it (tools/microbench/mma_rate.cu, profiles/r2_mma_issue_rate.txt):
+//  * one warp gets a tcgen05.mma accepted only every ~105-115 clk whatever its size (N <= 128): 12 small MMAs per 24 KB
+//    chunk from ONE issuer (the first round-2 version) cost ~1300 clk of issue time against the ~900 clk the chunk takes to
+//    arrive from HBM at the SM's share of the bandwidth.  Issuers in different warps overlap, so the products are divided between two warps, each
+//    owning its accumulators (the accumulation order inside every accumulator stays fixed => deterministic results);
+//  * with both operands in shared memory a chunk moves ~144 KB through the SM's 128 B/clk shared-memory port (TMA write,
+//    split read + lo write, three MMAs re-reading the 16 KB x tile) -- 1150 clk.  Here the convert warps read the raw x
+//    tile ONCE, split it in registers and park (hi, lo) in TMEM with tcgen05.st; only the template tiles are MMA operands
+//    in shared memory: ~80 KB per chunk.
+//
+// Per K-step (8 channels):  issuer A:  [main | c1] += x_hi * [z_hi ; z_lo]^T   (one N = 128 MMA: z_lo is written right
+//                                                                              behind the raw z tile of the stage)
+//                           issuer B:  c2 += x_lo * z_hi^T                     (N = 64)
+// and the epilogue writes main + (c1 + c2).  TMEM (512 columns): two accumulator sets of 192 columns, then two A slots of
+// (32 hi + 32 lo) columns.
+// ------------------------------------------------------------------------------------------
+constexpr int kCtsStages = 6;
+constexpr int kCtsSlots = 2;
+constexpr int kCtsStageBytes = kCorrABytes + 2 * kCorrBBytes;  // x raw | z raw | z lo
+constexpr int kCtsThreads = 15 * 32;  // producer, issuer A, 8 convert warps, 4 epilogue warps, issuer B
+constexpr int kCtsSmemBytes = kCtsStages * kCtsStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
+#ifdef FEAR_CORR_ABLATE
+// profiling build only: bit mask of pipeline roles that skip their work (barrier traffic kept) -- tools/corr_ablate.py
+__device__ int g_corr_ablate = 0;
+#define CORR_ABL(bit) (abl & (bit))
+#else
+#define CORR_ABL(bit) false
+#endif
+
+__global__ void __launch_bounds__(kCtsThreads, 1)
+corr_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                float* __restrict__ cat, int num_frames, int z_mod) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // offset arithmetic keeps LDS/STS
-  uint8_t* lo_buf = smem + kCorrStages * kCorrStageBytes;  // [2][x_lo 16 KB | z_lo 8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_buf + 2 * kCorrLoBytes);
-  uint64_t* full = bars;                       // [stages] TMA landed
-  uint64_t* empty = bars + kCorrStages;        // [stages] MMAs reading the stage have completed
-  uint64_t* split = bars + 2 * kCorrStages;    // [2] lo buffer written
-  uint64_t* lo_empty = split + 2;              // [2] MMAs reading the lo buffer have completed
-  uint64_t* acc_full = lo_empty + 2;           // [2] accumulator complete
-  uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained by the epilogue
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCtsStages * kCtsStageBytes);
+  uint64_t* full = bars;                          // [stages] TMA landed
+  uint64_t* empty = bars + kCtsStages;            // [stages] x tile read by the 8 convert warps + z tiles read by both issuers' MMAs
+  uint64_t* slot_full = bars + 2 * kCtsStages;    // [slots] (hi, lo) of x in TMEM and z_lo in smem written (8 warps)
+  uint64_t* slot_empty = slot_full + kCtsSlots;   // [slots] both issuers' MMAs reading the slot have completed
+  uint64_t* acc_full = slot_empty + kCtsSlots;    // [2] (both issuers)
+  uint64_t* acc_empty = acc_full + 2;             // [2] (4 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB (20 mbarriers + the TMEM slot < 256 B)
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + 256;  // 4 warps x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = num_frames * 2;
+  constexpr int kChunks = 256 / kCorrChunk;
+  constexpr uint32_t kColSlots = 384;
+#ifdef FEAR_CORR_ABLATE
+  const int abl = g_corr_ablate;
+#endif
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kCorrTmemCols);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   if (threadIdx.x == 64) {
-    for (int s = 0; s < kCorrStages; ++s) {
+    for (int s = 0; s < kCtsStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 10);
+    }
+    for (int a = 0; a < kCtsSlots; ++a) {
+      mbar_init(&slot_full[a], 8);
+      mbar_init(&slot_empty[a], 2);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&split[a], kCorrSplitThreads / 32);
-      mbar_init(&lo_empty[a], 1);
-      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_full[a], 2);
       mbar_init(&acc_empty[a], 4);
     }
     fence_mbar_init();
@@ -91,13 +111,11 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();  // the next kernel may start its prologue on SMs we have left
-  pdl_wait();     // everything above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_trigger();
+  pdl_wait();
 
-  auto a_hi = [&](int s) { return smem + s * kCorrStageBytes; };
-  auto b_hi = [&](int s) { return smem + s * kCorrStageBytes + kCorrABytes; };
-  auto a_lo = [&](int q) { return lo_buf + (q & 1) * kCorrLoBytes; };
-  auto b_lo = [&](int q) { return lo_buf + (q & 1) * kCorrLoBytes + kCorrABytes; };
+  auto st_x = [&](int s) { return smem + s * kCtsStageBytes; };
+  auto st_z = [&](int s) { return smem + s * kCtsStageBytes + kCorrABytes; };  // raw (= hi) tile, lo tile right behind it
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -107,47 +125,45 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int frame = t >> 1, half = t & 1;
         const int arow = frame * 256 + half * 128;
-        const int brow = z_mod ? (frame % z_mod) * 64 : 0;  // z_mod = 0: one template for every frame
-        for (int c = 0; c < 256 / kCorrChunk; ++c) {
+        const int brow = z_mod ? (frame % z_mod) * 64 : 0;
+        for (int c = 0; c < kChunks; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], kCorrABytes + kCorrBBytes);
-          tma_load_2d(a_hi(stage), &tmA, &full[stage], c * kCorrChunk, arow);
-          tma_load_2d(b_hi(stage), &tmB, &full[stage], c * kCorrChunk, brow);
-          if (++stage == kCorrStages) {
+          tma_load_2d(st_x(stage), &tmA, &full[stage], c * kCorrChunk, CORR_ABL(8) ? (int)(blockIdx.x & 1) * 128 : arow);
+          tma_load_2d(st_z(stage), &tmB, &full[stage], c * kCorrChunk, brow);
+          if (++stage == kCtsStages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+  } else if (warp == 1 || warp == 14) {
+    // ============================ MMA issuers: A (warp 1) = x_hi products, B (warp 14) = x_lo product ============================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      const bool issuer_b = warp == 14;
+      const uint32_t idesc = issuer_b ? umma_idesc_tf32(128, 64) : umma_idesc_tf32(128, 128);
       int stage = 0, acc = 0, q = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t acc_phase = 0, phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * 128;  // main accumulator; +64 = correction accumulator
-        for (int c = 0; c < 256 / kCorrChunk; ++c, ++q) {
-          mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> the stage has landed)
+        const uint32_t d = tmem_base + acc * 192 + (issuer_b ? 128 : 0);  // A: [main | c1] (128 columns); B: c2 (64)
+        for (int c = 0; c < kChunks; ++c, ++q) {
+          const int slot = q % kCtsSlots;
+          mbar_wait(&full[stage], phase);  // z tile (raw = hi) landed
+          mbar_wait(&slot_full[slot], (uint32_t)((q / kCtsSlots) & 1));
           tc_fence_after();
-          const uint32_t ah = smem_u32(a_hi(stage)), al = smem_u32(a_lo(q));
-          const uint32_t bh = smem_u32(b_hi(stage)), bl = smem_u32(b_lo(q));
+          const uint32_t a = tmem_base + kColSlots + slot * 64 + (issuer_b ? 32 : 0);
+          const uint32_t bz = smem_u32(st_z(stage));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 4 K-steps of 8 tf32 (32 B) inside the 128-B swizzle row
-            const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
-            const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
-            // hi*hi into the main accumulator; the two 2^-11-scaled cross terms into their own accumulator
-            // so the (truncating) tensor-core adder rounds the big sum 3x less often
-            mma_tf32_ss(d, dah, dbh, idesc, (c | j) != 0);       // main += x_hi z_hi
-            mma_tf32_ss(d + 64, dah, dbl, idesc, (c | j) != 0);  // corr += x_hi z_lo
-            mma_tf32_ss(d + 64, dal, dbh, idesc, 1);             // corr += x_lo z_hi
+          for (int j = 0; j < 4; ++j) {
+            if (CORR_ABL(1)) break;
+            mma_tf32_ts(d, a + j * 8, umma_desc_k_sw128(bz + j * 32), idesc, (c | j) != 0);
           }
-          tc_commit(&empty[stage]);  // stage reusable once these MMAs have read it
-          tc_commit(&lo_empty[q & 1]);
-          if (++stage == kCorrStages) {
+          tc_commit(&empty[stage]);      // this issuer's reads of the stage's z tiles
+          tc_commit(&slot_empty[slot]);  // ... and of the TMEM A slot
+          if (++stage == kCtsStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -157,83 +173,102 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp < 2 + kCorrSplitThreads / 32) {
-    // ===================================== operand split ====================================
-    const int ts = threadIdx.x - 64;  // 0..255
+  } else if (warp < 10) {
+    // ============================ convert: smem fp32 -> TMEM (hi, lo), z -> z_lo ============================
+    // 8 warps: two per TMEM lane quadrant, each converting 16 of the 32 channels of its 32 rows
+    const int qd = warp & 3;            // TMEM lane quadrant of this warp
+    const int hh = (warp - 2) >> 2;     // which 16-channel half of the chunk
+    const int row = qd * 32 + lane;     // x-tile row handled by this thread (= TMEM lane)
+    const int ts = threadIdx.x - 64;    // 0..255
     int stage = 0, q = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      for (int c = 0; c < 256 / kCorrChunk; ++c, ++q) {
+      for (int c = 0; c < kChunks; ++c, ++q) {
+        const int slot = q % kCtsSlots;
         mbar_wait(&full[stage], phase);
-        mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer
-        float4* ah = reinterpret_cast<float4*>(a_hi(stage));
-        float4* al = reinterpret_cast<float4*>(a_lo(q));
-        {
+        mbar_wait(&slot_empty[slot], (uint32_t)(((q / kCtsSlots) & 1) ^ 1));
+        tc_fence_after();
+        if (!CORR_ABL(2)) {
+          const float4* xrow = reinterpret_cast<const float4*>(st_x(stage) + row * 128);
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < kCorrABytes / 16 / kCorrSplitThreads; ++i) {
-            const float4 v = ah[ts + i * kCorrSplitThreads];
-            // kind::tf32 reads only the top 19 bits of each word, so the raw tile already IS the hi operand
-            // (verified on B200: identical results with and without rewriting it); only lo is materialised.
-            float4 h, l;
-            split_tf32_trunc(v.x, h.x, l.x);
-            split_tf32_trunc(v.y, h.y, l.y);
-            split_tf32_trunc(v.z, h.z, l.z);
-            split_tf32_trunc(v.w, h.w, l.w);
-            al[ts + i * kCorrSplitThreads] = l;
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = xrow[(hh * 4 + j) ^ (row & 7)];  // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;  // what kind::tf32 reads from the raw word
+              hi[4 * j + e] = h;
+              lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+            }
           }
-          float4* bh = reinterpret_cast<float4*>(b_hi(stage));
-          float4* bl = reinterpret_cast<float4*>(b_lo(q));
+          const uint32_t tdst = tmem_base + kColSlots + slot * 64 + ((uint32_t)(qd * 32) << 16);
+          tmem_st_32x16(tdst + hh * 16, hi);
+          tmem_st_32x16(tdst + 32 + hh * 16, lo);
+          // template tile: lo = v - trunc(v) at the same swizzled positions (index-identical copy)
+          const float4* zsrc = reinterpret_cast<const float4*>(st_z(stage));
+          float4* zdst = reinterpret_cast<float4*>(st_z(stage) + kCorrBBytes);
 #pragma unroll
-          for (int i = 0; i < kCorrBBytes / 16 / kCorrSplitThreads; ++i) {
-            const float4 v = bh[ts + i * kCorrSplitThreads];
+          for (int i = 0; i < kCorrBBytes / 16 / 256; ++i) {
+            const float4 v = zsrc[ts + i * 256];
             float4 h, l;
             split_tf32_trunc(v.x, h.x, l.x);
             split_tf32_trunc(v.y, h.y, l.y);
             split_tf32_trunc(v.z, h.z, l.z);
             split_tf32_trunc(v.w, h.w, l.w);
-            bl[ts + i * kCorrSplitThreads] = l;
+            zdst[ts + i * 256] = l;
           }
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();  // z_lo: generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&split[q & 1]);
-        if (++stage == kCorrStages) {
+        if (lane == 0) {
+          mbar_arrive(&empty[stage]);  // this warp has read the stage's x tile
+          mbar_arrive(&slot_full[slot]);
+        }
+        if (++stage == kCtsStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
   } else {
-    // ===================================== epilogue =========================================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================================== epilogue (warps 10..13) =====================================
+    // TMEM -> registers -> per-warp smem staging (2 KB) -> 16-byte coalesced stores into cat[:, 256 + k]
+    const int qd = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4* stg = reinterpret_cast<float4*>(epi_stage + qd * 2048);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int frame = t >> 1, half = t & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(q * 32) << 16);
-      const long long row0 = (long long)frame * 256 + half * 128 + q * 32;
-      float4* stg = reinterpret_cast<float4*>(epi_stage + q * 2048);
+      const uint32_t taddr = tmem_base + acc * 192 + ((uint32_t)(qd * 32) << 16);
+      const long long row0 = (long long)frame * 256 + half * 128 + qd * 32;
 #pragma unroll
       for (int g = 0; g < 64; g += 16) {
-        uint32_t m[16], sm[16];
-        tmem_ld_32x16(taddr + g, m);        // main (hi*hi)
-        tmem_ld_32x16(taddr + 64 + g, sm);  // correction (lo*hi + hi*lo)
+        uint32_t m[16], c1[16], c2[16];
+        if (CORR_ABL(4)) {
+          if (g == 48) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          }
+          continue;
+        }
+        tmem_ld_32x16(taddr + g, m);
+        tmem_ld_32x16(taddr + 64 + g, c1);
+        tmem_ld_32x16(taddr + 128 + g, c2);
         tmem_ld_wait();
         if (g == 48) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);  // accumulators free for tile t+2
         }
-        // per-warp 32 x 16 transpose through smem so each store instruction writes 8 rows x 64 B
+        auto sum = [&](int i) { return __uint_as_float(m[i]) + (__uint_as_float(c1[i]) + __uint_as_float(c2[i])); };
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] =
-              make_float4(__uint_as_float(m[4 * j]) + __uint_as_float(sm[4 * j]),
-                          __uint_as_float(m[4 * j + 1]) + __uint_as_float(sm[4 * j + 1]),
-                          __uint_as_float(m[4 * j + 2]) + __uint_as_float(sm[4 * j + 2]),
-                          __uint_as_float(m[4 * j + 3]) + __uint_as_float(sm[4 * j + 3]));
+          stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(sum(4 * j), sum(4 * j + 1), sum(4 * j + 2), sum(4 * j + 3));
         __syncwarp();
         const int j = lane & 3;
 #pragma unroll
@@ -252,7 +287,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kCorrTmemCols);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -271,7 +306,7 @@ inline int init() {
   st.num_sms = p.multiProcessorCount;
   st.inited = true;
   if (resolve_driver()) return 0;  // tcgen05 path stays unavailable; the FFMA path still works
-  if (cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmemBytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(corr_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtsSmemBytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -294,7 +329,8 @@ inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int 
   if (r) return r;
   const int tiles = frames * 2;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (launch_pdl(corr_tc_kernel, dim3(grid), dim3(kCorrThreads), kCorrSmemBytes, s, tmA, tmB, cat, frames, Bz == 1 ? 0 : B) != cudaSuccess)
+  if (launch_pdl(corr_ts_kernel, dim3(grid), dim3(kCtsThreads), kCtsSmemBytes, s, tmA, tmB, cat, frames, Bz == 1 ? 0 : B) !=
+      cudaSuccess)
     return -23;
   return 0;
 }

@@ -14,12 +14,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from feartracker_b200 import _lib  # noqa: E402
 
 
+def _select_corr(lib, impl):
+    _lib.check(lib.fear_set_option(None, b"corr", impl.encode()), "fear_set_option")
+
+
 def corr_case(lib, B, Bz, impl, seed=0):
     g = torch.Generator().manual_seed(seed)
     zt = torch.randn(Bz, 64, 256, generator=g)
     cat = torch.randn(B, 256, 320, generator=g)
     ref = torch.einsum("bpc,bkc->bpk", cat[:, :, :256].double(), (zt if Bz == B else zt.expand(B, 64, 256)).double())
-    _lib.check(lib.fear_set_option(None, b"corr", impl.encode()), "fear_set_option")
+    _select_corr(lib, impl)
     zc, cc = zt.cuda(), cat.cuda()
     _lib.check(lib.fear_corr_nhwc_f32(zc.data_ptr(), Bz, cc.data_ptr(), B, torch.cuda.current_stream().cuda_stream),
                "fear_corr_nhwc_f32")
@@ -81,7 +85,7 @@ def net_case(pw, corr):
 
 def corr_perf(lib, impl, B=256, iters=50):
     """Timing only: the channels-last correlation kernel on B frames, rotating over 4 buffers (> L2)."""
-    _lib.check(lib.fear_set_option(None, b"corr", impl.encode()), "fear_set_option")
+    _select_corr(lib, impl)
     zt = torch.randn(B, 64, 256, device="cuda")
     cats = [torch.randn(B, 256, 320, device="cuda") for _ in range(4)]
     st = torch.cuda.current_stream().cuda_stream

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_tcgen05.py -q -x -k corr 2>&1 | tail -3
-python tests/tc_check.py corrperf tcgen05 ffma 2>&1 | tail -1 | cut -c1-400
-python bench.py --steps 20 --warmup 5 --no-stream --no-cpu-baseline > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err
+timeout 600 python -m pytest tests/test_gpu_tcgen05.py -q -x -k corr 2>&1 | tail -3
+timeout 300 python tests/tc_check.py corrperf tcgen05 ffma 2>&1 | tail -1 | cut -c1-400
+timeout 600 python bench.py --steps 20 --warmup 5 --no-stream --no-cpu-baseline > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/bench_q.json"))
