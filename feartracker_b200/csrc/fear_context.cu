@@ -1165,6 +1165,29 @@ extern "C" int fear_debug_corr_ablate(int mask) {
 }
 #endif
 
+#ifdef FEAR_PW_ABLATE
+// Profiling build only (FEAR_NVCC_FLAGS=-DFEAR_PW_ABLATE): see kernels_tc.cuh / tools/pw_ablate.py.
+extern "C" int fear_debug_pw_ablate(int mask) {
+  CUDA_TRY(cudaMemcpyToSymbol(tc::g_pw_ablate, &mask, sizeof(int)));
+  return 0;
+}
+#endif
+
+#ifdef FEAR_PW_TIMING
+// Profiling build only (FEAR_NVCC_FLAGS=-DFEAR_PW_TIMING): per-launch role cycle counters of pw_tc_kernel since the last
+// call (launch ordinal modulo 64); counters [64][32] u64, info [64][8] int.  Resets both.  tools/pw_timing.py
+extern "C" int fear_debug_pw_timing(unsigned long long* counters, int* info) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (counters) CUDA_TRY(cudaMemcpyFromSymbol(counters, tc::g_pw_timing, sizeof(unsigned long long) * 64 * 32));
+  if (info) memcpy(info, tc::pw_timing_info(), sizeof(tc::PwTimingInfo) * 64);
+  static unsigned long long zeros[64 * 32];
+  CUDA_TRY(cudaMemcpyToSymbol(tc::g_pw_timing, zeros, sizeof(zeros)));
+  int n = tc::pw_timing_next();
+  tc::pw_timing_next() = 0;
+  return n;
+}
+#endif
+
 extern "C" int64_t fear_launch_count(const FearContext* c) { return c ? c->launches : 0; }
 extern "C" int64_t fear_generation(const FearContext* c) { return c ? c->generation : -1; }
 

@@ -344,6 +344,39 @@ inline int launch_corr(cudaStream_t s, const float* zt, int Bz, float* cat, int 
 // (S chosen from the stage size).  TMA zero-fills the K tail (Cin not a multiple of 32), rows >= M
 // and weight rows >= N.  Two TMEM accumulators of NT columns each overlap epilogue and MMA.
 // ------------------------------------------------------------------------------------------
+#ifdef FEAR_PW_ABLATE
+// profiling build only: roles of pw_tc_kernel that skip their work (barrier traffic kept; results are garbage) --
+// tools/pw_ablate.py.  1 = MMAs, 2 = operand split / depthwise compute + A-tile writes, 4 = epilogue, 8 = weight loads,
+// 16 = activation (A tile / depthwise input box) loads
+__device__ int g_pw_ablate = 0;
+#define PW_ABL(bit) (pw_abl & (bit))
+#else
+#define PW_ABL(bit) false
+#endif
+
+#ifdef FEAR_PW_TIMING
+// profiling build only: per-launch, per-role cycle counters (summed over CTAs) -- tools/pw_timing.py
+__device__ unsigned long long g_pw_timing[64][32];
+inline int& pw_timing_next() {
+  static int n = 0;
+  return n;
+}
+struct PwTimingInfo { int M, N, K, dwk, map_w, grid, tiles, chunks; };
+inline PwTimingInfo* pw_timing_info() {
+  static PwTimingInfo info[64];
+  return info;
+}
+#define PWT(v) const long long v = clock64()
+#define PWT_ACC(slot, a, b) pwt[slot] += (unsigned long long)((b) - (a))
+#define PWT_FLUSH(lo, hi)                                                                              \
+  if (lane == 0)                                                                                       \
+    for (int k_ = (lo); k_ < (hi); ++k_) atomicAdd(&g_pw_timing[p.timing_id & 63][k_], pwt[k_])
+#else
+#define PWT(v)
+#define PWT_ACC(slot, a, b)
+#define PWT_FLUSH(lo, hi)
+#endif
+
 struct PwParams {
   const float* bias;  // [N] or null
   const float* R;     // residual [M][ldr] or null
@@ -356,6 +389,9 @@ struct PwParams {
   int dw_relu, dw_bias;  // ReLU / bias of the depthwise stage
   int box_bytes;         // bytes of one (tile rows + DWK - 1) x (map width + DWK - 1) x 32-channel input box
   int map_w;             // fused depthwise: square map side, 16 (tile = 8 rows x 16) or 32 (tile = 4 rows x 32)
+#ifdef FEAR_PW_TIMING
+  int timing_id;
+#endif
   int w_region;   // > 0: the (hi, lo) weight tile is loaded ONCE into the first w_region bytes of smem (layers with one
                   // N tile and one K chunk) and the ring stages hold activations only
 };
@@ -396,6 +432,14 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float* sbias = reinterpret_cast<float*>(epi_stage + 8 * 2 * 2048);  // [2][256] per accumulator stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FEAR_PW_ABLATE
+  const int pw_abl = g_pw_ablate;
+#endif
+#ifdef FEAR_PW_TIMING
+  unsigned long long pwt[32];
+#pragma unroll
+  for (int k_ = 0; k_ < 32; ++k_) pwt[k_] = 0;
+#endif
   const int num_m_tiles = (p.M + 127) >> 7;
   const int num_tiles = num_m_tiles * p.num_n_tiles;
   const int w_bytes = p.NT * 128;
@@ -456,25 +500,31 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tma_load_2d(w_hi(0), &tmWh, w_full, 0, 0);
         tma_load_2d(w_lo(0), &tmWl, w_full, 0, 0);
       }
+      PWT(tp0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int mt = t / p.num_n_tiles, nt = t - mt * p.num_n_tiles;
         for (int c = 0; c < p.num_chunks; ++c) {
+          PWT(tp1);
           mbar_wait(&empty[stage], phase ^ 1);
+          PWT(tp2);
+          PWT_ACC(0, tp1, tp2);
           if constexpr (DWK > 0) {
             // weight tiles only: the input box of a stage is re-filled by the depthwise group that owns the stage as soon
             // as it has read it (well before the MMAs release the stage), see below
-            mbar_arrive_expect_tx(&wfl[stage], 2 * w_bytes);
-            tma_load_2d(w_hi(stage), &tmWh, &wfl[stage], c * 32, nt * p.NT);
-            tma_load_2d(w_lo(stage), &tmWl, &wfl[stage], c * 32, nt * p.NT);
+            mbar_arrive_expect_tx(&wfl[stage], PW_ABL(8) ? 0 : 2 * w_bytes);
+            if (!PW_ABL(8)) {
+              tma_load_2d(w_hi(stage), &tmWh, &wfl[stage], c * 32, nt * p.NT);
+              tma_load_2d(w_lo(stage), &tmWl, &wfl[stage], c * 32, nt * p.NT);
+            }
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
             }
             continue;
           }
-          mbar_arrive_expect_tx(&full[stage], resident_w ? kCorrABytes : kCorrABytes + 2 * w_bytes);
-          tma_load_2d(a_hi(stage), &tmA, &full[stage], c * 32, mt * 128);
-          if (!resident_w) {
+          mbar_arrive_expect_tx(&full[stage], (PW_ABL(16) ? 0 : kCorrABytes) + ((resident_w || PW_ABL(8)) ? 0 : 2 * w_bytes));
+          if (!PW_ABL(16)) tma_load_2d(a_hi(stage), &tmA, &full[stage], c * 32, mt * 128);
+          if (!resident_w && !PW_ABL(8)) {
             tma_load_2d(w_hi(stage), &tmWh, &full[stage], c * 32, nt * p.NT);
             tma_load_2d(w_lo(stage), &tmWl, &full[stage], c * 32, nt * p.NT);
           }
@@ -484,6 +534,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      PWT(tp3);
+      PWT_ACC(1, tp0, tp3);
+      PWT_FLUSH(0, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -492,23 +545,33 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0, acc = 0, q = 0;
       uint32_t phase = 0, acc_phase = 0;
       if (resident_w) mbar_wait(w_full, 0);
+      PWT(tm0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        PWT(tm1);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        PWT(tm2);
+        PWT_ACC(2, tm1, tm2);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * p.acc_stride;  // main; + NT = correction accumulator (split_acc)
         for (int c = 0; c < p.num_chunks; ++c, ++q) {
+          PWT(tm3);
           if constexpr (DWK == 0) {
             mbar_wait(&split[q & 1], (uint32_t)((q >> 1) & 1));  // lo buffer written (=> stage landed)
           } else {
             mbar_wait(&split[stage], phase);  // depthwise output (hi, lo) written
+            PWT(tm3b);
+            PWT_ACC(21, tm3, tm3b);
             mbar_wait(&wfl[stage], phase);    // weight tiles landed
           }
+          PWT(tm4);
+          PWT_ACC(3, tm3, tm4);
           tc_fence_after();
           const uint32_t ah = smem_u32(a_hi(stage));
           const uint32_t al = DWK == 0 ? smem_u32(lo_buf + (q & 1) * kCorrABytes) : smem_u32(a_lo(stage));
           const uint32_t bh = smem_u32(w_hi(stage)), bl = smem_u32(w_lo(stage));
           const int ksteps = (c == p.num_chunks - 1) ? p.last_ksteps : 4;  // K tail: skip all-zero K-steps
           for (int j = 0; j < ksteps; ++j) {
+            if (PW_ABL(1)) break;
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
             // short K (<= 2 chunks): a handful of accumulations, the truncating adder is harmless and a single
@@ -526,6 +589,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           tc_commit(&empty[stage]);
           if constexpr (DWK == 0) tc_commit(&lo_empty[q & 1]);
+          PWT(tm5);
+          PWT_ACC(4, tm4, tm5);
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -535,22 +600,30 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      PWT(tm6);
+      PWT_ACC(5, tm0, tm6);
+      PWT_FLUSH(2, 6);
+      PWT_FLUSH(21, 22);
     }
   } else if (warp < 10) {
     const int ts = threadIdx.x - 64;  // 0..255
     int stage = 0;
     uint32_t phase = 0;
     if constexpr (DWK > 0) {
-      // ---- fused depthwise: group g (4 warps) owns stage g (S == 2); thread = (4-channel group, 2 x 4 pixel block) ----
-      constexpr int K = DWK, TX = 4, TY = 2, NIN = TX + K - 1, NR = TY + K - 1;
-      constexpr int IW = MW + K - 1, PXN = MW / TX;  // 16 positions: 4 across x 4 down (16x16) | 8 x 2 (32x32)
+      // ---- fused depthwise: group g (4 warps) owns stage g (S == 2); thread = (2-channel pair, 2 x 8 pixel block) ----
+      // These kernels are bound by the shared-memory port (tools/pw_timing.py: the depthwise pass is 60 % of the kernel and
+      // slows down with everything else that moves through smem).  A thread owning 2 channels x 16 pixels instead of
+      // 4 channels x 8 pixels issues the same FFMA2s but 1/3 fewer LDS wavefronts: the halo of a 2 x 8 block is smaller
+      // and a weight is fetched once per 16 pixels (5x5: 194 instead of 292 wavefronts per warp and chunk).
+      constexpr int K = DWK, TX = 8, TY = 2, NIN = TX + K - 1, NR = TY + K - 1;
+      constexpr int IW = MW + K - 1, PXN = MW / TX;  // 8 positions: 2 across x 4 down (16x16) | 4 x 2 (32x32)
       const int group = (warp - 2) >> 2, gw = (warp - 2) & 3;
-      const int cg = lane & 7, pos = gw * 4 + (lane >> 3);
+      const int c2 = lane & 15, pos = gw * 2 + (lane >> 4);
       const int x0 = (pos % PXN) * TX, r0 = (pos / PXN) * TY;
       // The group's leader thread issues the TMA of the group's NEXT input box (chunk + 2, same stage) as soon as all
       // four warps have read the current one -- not when the MMAs release the stage: the box is ~1/3 of a stage and its
       // load latency (~2 us under load) was fully exposed with two stages.
-      auto issue_box = [&](int t2, int c2) {
+      auto issue_box = [&](int t2, int c2, bool l2_only) {
         while (c2 >= p.num_chunks) {
           c2 -= p.num_chunks;
           t2 += gridDim.x;
@@ -558,37 +631,49 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (t2 >= num_tiles) return;
         constexpr int th = 128 / MW, tpf = MW / th;
         const int mt2 = t2 / p.num_n_tiles, st = group;  // S == 2: stage = chunk & 1 = group
-        mbar_arrive_expect_tx(&full[st], p.box_bytes + DWK * DWK * 128 + (p.dw_bias ? 128 : 0));
-        tma_load_4d(dw_box(st), &tmA, &full[st], c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
+        if (l2_only) {
+          // the shared-memory box is still being read: start the HBM -> L2 leg of the next box now, so that the TMA load
+          // issued after the depthwise pass finds its lines in L2 (the group's box round trip is exposed, S == 2)
+          if (!PW_ABL(32)) tma_prefetch_4d(&tmA, c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
+          return;
+        }
+        mbar_arrive_expect_tx(&full[st], (PW_ABL(16) ? 0 : p.box_bytes) + DWK * DWK * 128 + (p.dw_bias ? 128 : 0));
+        if (!PW_ABL(16)) tma_load_4d(dw_box(st), &tmA, &full[st], c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
         tma_load_2d(dw_wts(st), &tmDW, &full[st], c2 * 32, 0);
         if (p.dw_bias) tma_load_2d(dw_bia(st), &tmDB, &full[st], c2 * 32, 0);
       };
       const bool leader = gw == 0 && lane == 0;
-      if (leader) issue_box(blockIdx.x, group);  // the group's first chunk
+      if (leader) issue_box(blockIdx.x, group, false);  // the group's first chunk
       int chunk = 0;
+      PWT(td0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int c = 0; c < p.num_chunks; ++c, ++chunk) {
           if ((chunk & 1) == group) {
+            PWT(td1);
             mbar_wait(&full[stage], phase);
-            const F4* in4 = reinterpret_cast<const F4*>(dw_box(stage));
-            const F4* w4 = reinterpret_cast<const F4*>(dw_wts(stage));
-            F4 acc[TY][TX], bias4;
-            if (p.dw_bias) bias4 = reinterpret_cast<const F4*>(dw_bia(stage))[cg];
-            else bias4.lo = bias4.hi = 0ull;
+            PWT(td2);
+            PWT_ACC(6, td1, td2);
+            if (leader) issue_box(t, c + 2, true);
+            typedef unsigned long long U2;  // two packed fp32 channels
+            const U2* in2 = reinterpret_cast<const U2*>(dw_box(stage));
+            const U2* w2 = reinterpret_cast<const U2*>(dw_wts(stage));
+            U2 acc[TY][TX];
+            const U2 bias2 = p.dw_bias ? reinterpret_cast<const U2*>(dw_bia(stage))[c2] : 0ull;
 #pragma unroll
             for (int y = 0; y < TY; ++y)
 #pragma unroll
-              for (int i = 0; i < TX; ++i) acc[y][i] = bias4;
-            F4 wk[K][K];
-            const F4* base = in4 + (r0 * IW + x0) * 8 + cg;
+              for (int i = 0; i < TX; ++i) acc[y][i] = bias2;
+            U2 wk[K][K];
+            const U2* base = in2 + (r0 * IW + x0) * 16 + c2;
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-              F4 v[NIN];
+              if (PW_ABL(2)) break;
+              U2 v[NIN];
 #pragma unroll
-              for (int i = 0; i < NIN; ++i) v[i] = base[(r * IW + i) * 8];
+              for (int i = 0; i < NIN; ++i) v[i] = base[(r * IW + i) * 16];
               if (r < K) {
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) wk[r < K ? r : 0][kx] = w4[(r * K + kx) * 8 + cg];
+                for (int kx = 0; kx < K; ++kx) wk[r < K ? r : 0][kx] = w2[(r * K + kx) * 16 + c2];
               }
 #pragma unroll
               for (int y = 0; y < TY; ++y) {
@@ -596,48 +681,51 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (ky >= 0 && ky < K) {
 #pragma unroll
                   for (int kx = 0; kx < K; ++kx) {
-                    const F4 k = wk[(ky >= 0 && ky < K) ? ky : 0][kx];
+                    const U2 k = wk[(ky >= 0 && ky < K) ? ky : 0][kx];
 #pragma unroll
-                    for (int i = 0; i < TX; ++i) ffma2(acc[y][i].lo, v[i + kx].lo, k.lo);
-#pragma unroll
-                    for (int i = 0; i < TX; ++i) ffma2(acc[y][i].hi, v[i + kx].hi, k.hi);
+                    for (int i = 0; i < TX; ++i) ffma2(acc[y][i], v[i + kx], k);
                   }
                 }
               }
             }
             __syncwarp();
+            PWT(td3);
+            PWT_ACC(7, td2, td3);
             if (lane == 0) mbar_arrive(&box_empty[stage]);  // this warp has read the box
             if (leader) {
               mbar_wait(&box_empty[stage], phase);
-              issue_box(t, c + 2);
+              issue_box(t, c + 2, false);
             }
+            PWT(td4);
+            PWT_ACC(8, td3, td4);
             mbar_wait(&empty[stage], phase ^ 1);  // the MMAs of this stage's previous chunk have read its A tiles
+            PWT(td5);
+            PWT_ACC(9, td4, td5);
             uint8_t* ah = a_hi(stage);
             uint8_t* al = a_lo(stage);
 #pragma unroll
             for (int y = 0; y < TY; ++y)
 #pragma unroll
               for (int i = 0; i < TX; ++i) {
-                float4 v = f4_to_float4(acc[y][i]);
+                if (PW_ABL(2)) break;
+                float2 v = make_float2(__uint_as_float((uint32_t)acc[y][i]), __uint_as_float((uint32_t)(acc[y][i] >> 32)));
                 if (p.dw_relu) {
                   v.x = fmaxf(v.x, 0.f);
                   v.y = fmaxf(v.y, 0.f);
-                  v.z = fmaxf(v.z, 0.f);
-                  v.w = fmaxf(v.w, 0.f);
                 }
-                float4 h, l;
+                float2 h, l;
                 split_tf32_trunc(v.x, h.x, l.x);
                 split_tf32_trunc(v.y, h.y, l.y);
-                split_tf32_trunc(v.z, h.z, l.z);
-                split_tf32_trunc(v.w, h.w, l.w);
-                const int R = (r0 + y) * MW + x0 + i;                         // A-tile row = pixel inside the tile
-                const int off = R * 128 + ((cg ^ (R & 7)) << 4);              // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
-                *reinterpret_cast<float4*>(ah + off) = v;                     // raw fp32 = hi operand (hardware truncation)
-                *reinterpret_cast<float4*>(al + off) = l;
+                const int R = (r0 + y) * MW + x0 + i;                                         // A-tile row = pixel inside the tile
+                const int off = R * 128 + (((c2 >> 1) ^ (R & 7)) << 4) + ((c2 & 1) << 3);     // SWIZZLE_128B: 16-byte chunk ^ (row % 8)
+                *reinterpret_cast<float2*>(ah + off) = v;                                     // raw fp32 = hi operand (hardware truncation)
+                *reinterpret_cast<float2*>(al + off) = l;
               }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[stage]);
+            PWT(td6);
+            PWT_ACC(10, td5, td6);
           }
           if (++stage == S) {
             stage = 0;
@@ -645,16 +733,26 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      PWT(td7);
+      PWT_ACC(11, td0, td7);
+      if (gw == 0 && group == 0) { PWT_FLUSH(6, 12); }
     } else {
     int q = 0;
+    PWT(ts0);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int c = 0; c < p.num_chunks; ++c, ++q) {
+        PWT(ts1);
         mbar_wait(&full[stage], phase);
+        PWT(ts2);
+        PWT_ACC(6, ts1, ts2);
         mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer
+        PWT(ts3);
+        PWT_ACC(9, ts2, ts3);
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
         float4* al = reinterpret_cast<float4*>(lo_buf + (q & 1) * kCorrABytes);
 #pragma unroll
         for (int i = 0; i < kCorrABytes / 16 / 256; ++i) {
+          if (PW_ABL(2)) break;
           const float4 v = ah[ts + i * 256];  // the raw tile is the hi operand as it stands (hardware truncation)
           float4 h, l;
           split_tf32_trunc(v.x, h.x, l.x);
@@ -666,12 +764,17 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split[q & 1]);
+        PWT(ts4);
+        PWT_ACC(10, ts3, ts4);
         if (++stage == S) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
+    PWT(ts5);
+    PWT_ACC(11, ts0, ts5);
+    if (warp == 2) { PWT_FLUSH(6, 12); }
     }
   } else {
     // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
@@ -706,11 +809,15 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (t + (int)gridDim.x < num_tiles) bias_next = load_bias(t + gridDim.x);
         asm volatile("bar.sync 1, 256;" ::: "memory");  // named barrier over the 8 epilogue warps
       }
+      PWT(te1);
       mbar_wait(&acc_full[acc], acc_phase);
+      PWT(te2);
+      PWT_ACC(18, te1, te2);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * p.acc_stride + ((uint32_t)(q * 32) << 16);
       const float* sb = sbias + acc * 256;
-      if (!p.R && !p.split_acc) {
+      if (PW_ABL(4)) {
+      } else if (!p.R && !p.split_acc) {
         // short-K layers (wide, epilogue-bound): 32 columns per TMEM round trip, single accumulator
         for (int g = hsel * 32; g < p.NT; g += 64) {
           uint32_t r32[32];
@@ -832,10 +939,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      PWT(te3);
+      PWT_ACC(19, te2, te3);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (!p.R) tma_store_wait<0>();  // all bulk stores of this warp have completed before the CTA exits
+    if (warp == 10) { PWT_FLUSH(18, 20); }
   }
 
   tc_fence_before();
@@ -922,6 +1032,10 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
   const int smem_bytes = p.w_region + 2 * kCorrABytes + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
+#ifdef FEAR_PW_TIMING
+  p.timing_id = pw_timing_next()++;
+  pw_timing_info()[p.timing_id & 63] = {M, N, K, 0, 0, grid, tiles, p.num_chunks};
+#endif
   if (launch_pdl(pw_tc_kernel<0>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA, tmA, p) !=
       cudaSuccess)
     return -23;
@@ -985,6 +1099,10 @@ inline int launch_pw_dw(cudaStream_t s, const float* X, int B, int dw_k, const f
   const int tiles = (M / 128) * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const size_t smem_bytes = (size_t)2 * p.stage_bytes + 1024 + kPwTailBytes;
+#ifdef FEAR_PW_TIMING
+  p.timing_id = pw_timing_next()++;
+  pw_timing_info()[p.timing_id & 63] = {M, N, K, dw_k, map_w, grid, tiles, p.num_chunks};
+#endif
   cudaError_t e;
   if (map_w == 16)
     e = dw_k == 5 ? launch_pdl(pw_tc_kernel<5, 16>, dim3(grid), dim3(kPwThreads), smem_bytes, s, tmX, tmWh, tmWl, tmC, tmDW, tmDB, p)
