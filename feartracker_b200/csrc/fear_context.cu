@@ -16,6 +16,7 @@
 #include "kernels_dw_tma.cuh"
 #include "kernels_stem_fused.cuh"
 #include "kernels_irf_fused.cuh"
+#include "kernels_dwpw_small.cuh"
 
 using namespace fear;
 
@@ -65,9 +66,10 @@ enum Impl { IMPL_FFMA = 0, IMPL_TC = 1 };  // CUDA cores (FFMA baseline / fallba
 struct Options {
   int corr = -1;  // -1 = auto: tcgen05 when the tensor-core path initialised on this device, else CUDA cores
   int pw = -1;
-  int fuse_dwpw = 7;  // bit mask: 1 = IRF blocks on 16x16 maps, 4 = also the IRF blocks on 32x32 maps, 2 = head SepConvs run
+  int fuse_dwpw = 15; // bit mask: 1 = IRF blocks on 16x16 maps, 4 = also the IRF blocks on 32x32 maps, 2 = head SepConvs run
                       // depthwise + 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK, MW>): bit-identical to the unfused pair,
-                      // the depthwise maps are never written.  Round 2: 3.56 -> 3.40 ms / step, -2.3 GB DRAM traffic / step
+                      // the depthwise maps are never written.  Round 2: 3.56 -> 3.40 ms / step, -2.3 GB DRAM traffic / step.
+                      // 8 = the expand-1 blocks (xif2_2, xif2_3: dw 3x3 -> 1x1 24 -> 24 -> + x) as one CUDA-core kernel
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse_irf = 1;   // 1: xif2_0 (expand -> depthwise s2 -> project) as ONE tcgen05 kernel (irf_s2_fused_kernel)
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel,
@@ -374,6 +376,24 @@ static int run_blocks(FearContext* c, cudaStream_t s, float* X, int B, int& h, i
         FEAR_TRY(check_launch("tc::irf_s2_fused_kernel"));
         h /= 2;
         w /= 2;
+        float* t = X;
+        X = Y;
+        Y = t;
+        continue;
+      }
+    }
+    if ((c->opt.fuse_dwpw & 8) && tc::available() && !sp.has_pw() && sp.stride == 1 && sp.k == 3 && sp.cin == tc::kDpC &&
+        sp.cout == tc::kDpC && sp.residual() && bw.dw.b && bw.pwl.h_w && effective(c->opt.pw) != IMPL_FFMA) {
+      // expand-1 block: depthwise 3x3 + 1x1 + residual in one kernel (the depthwise map stays in shared memory)
+      LaunchScope scope(c, ST_BACKBONE_DW, s);
+      PwSmallWeights<tc::kDpC, tc::kDpC> pw;
+      for (int o = 0; o < tc::kDpC; ++o)
+        for (int k = 0; k < tc::kDpC; ++k) pw.w[k * tc::kDpC + o] = bw.pwl.h_w[o * tc::kDpC + k];
+      memcpy(pw.b, bw.pwl.h_b, sizeof(pw.b));
+      int r = tc::launch_dw3_pw24(s, X, bw.dw.w, bw.dw.b, pw, Y, B, h, w, tc::num_sms());
+      if (r < 0) return set_err(FEAR_EINVAL, "fused depthwise + 24x24 block launch failed (%d)", r);
+      if (r == 0) {
+        FEAR_TRY(check_launch("tc::dw3_pw24_fused_kernel"));
         float* t = X;
         X = Y;
         Y = t;
@@ -1107,7 +1127,7 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
     return 0;
   }
   if (!strcmp(key, "fuse_dwpw")) {
-    o.fuse_dwpw = atoi(value) & 7;  // bit 0: 16x16-stage backbone blocks, bit 1: the head's SepConvs, bit 2: also the 32x32-stage blocks
+    o.fuse_dwpw = atoi(value) & 15;  // bit 0: 16x16-stage backbone blocks, bit 1: the head's SepConvs, bit 2: also the 32x32-stage blocks, bit 3: expand-1 blocks
     return 0;
   }
   if (!strcmp(key, "fuse_stem")) {

@@ -159,9 +159,10 @@ int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* str
  *   "fuse_stem"    : "1" (default) stem + xif1_0 in one kernel | "0" four separate kernels
  *   "fuse_irf"     : "1" (default) xif2_0 (expand 1x1 -> depthwise 3x3 s2 -> project 1x1) in ONE tcgen05 kernel, the
  *                    6x expanded tensor never leaves the SM | "0" three kernels
- *   "fuse_dwpw"    : bit mask (default 7): 1 = IRF blocks on 16x16 maps, 4 = also those on 32x32 maps, 2 = head SepConvs run
- *                    their depthwise conv inside the 1x1 GEMM kernel (bit-identical to the two-kernel path; the depthwise
- *                    maps are never written)
+ *   "fuse_dwpw"    : bit mask (default 15): 1 = IRF blocks on 16x16 maps, 4 = also those on 32x32 maps, 2 = head SepConvs run
+ *                    their depthwise conv inside the 1x1 GEMM kernel, 8 = the expand-1 blocks (depthwise 3x3 -> 1x1 24 -> 24
+ *                    -> + x) run as one CUDA-core kernel; all bit-identical to the two-kernel paths (the depthwise maps are
+ *                    never written)
  *   "pdl"          : "1" (default) programmatic dependent launch (process-wide) */
 int fear_set_option(FearContext* h, const char* key, const char* value);
 /* Number of kernels launched by this handle since creation (for bench's gpu_launches). */

@@ -261,11 +261,12 @@ def test_fused_stem_block_is_bit_identical(net):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("mask", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("mask", ["0", "1", "2", "3", "7", "8"])
 def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
     """fuse_dwpw: depthwise + 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK>) -- bit 0: the 16x16-stage backbone blocks,
-    bit 2: also the 32x32-stage blocks, bit 1: the head's SepConvs; default 7 = all.  The depthwise values are computed in the same order as
-    dw_tma_kernel and the GEMM is the same MMA sequence, so switching either fusion off may not change a bit."""
+    bit 2: also the 32x32-stage blocks, bit 1: the head's SepConvs; bit 3: the expand-1 blocks xif2_2 / xif2_3 as one CUDA-core
+    kernel (dw3_pw24_fused_kernel); default 15 = all.  The depthwise values are computed in the same order as dw_tma_kernel and
+    the 1x1 convs are the same MMA / FMA sequences, so switching any fusion off may not change a bit."""
     zt, xt, _, _ = fo.synthetic_crops(3)
     zf = net.get_features(zt.cuda())
     ref_f = net.get_features(xt.cuda())
@@ -275,7 +276,7 @@ def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
         got_f = net.get_features(xt.cuda())
         got = net.track(xt.cuda(), zf)
     finally:
-        net.set_option("fuse_dwpw", "7")
+        net.set_option("fuse_dwpw", "15")
     assert torch.equal(ref_f, got_f), float((ref_f - got_f).abs().max())
     assert torch.equal(ref[R], got[R]) and torch.equal(ref[C], got[C])
 
