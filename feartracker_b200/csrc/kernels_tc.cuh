@@ -396,7 +396,7 @@ struct PwParams {
                   // N tile and one K chunk) and the ring stages hold activations only
 };
 
-constexpr int kPwThreads = 576;  // producer, MMA, 8 split warps, 8 epilogue warps
+constexpr int kPwThreads = 608;  // producer, MMA, 8 split / depthwise warps, 8 epilogue warps, depthwise-box producer
 
 // DWK = 0: plain 1x1 conv.  DWK = 3 | 5 (EXPERIMENTAL, opt-in "fuse_dwpw"; 16x16 maps, stride 1): the layer's input is
 // the output of a DWK x DWK depthwise conv that is never materialised -- the producer TMA-loads the depthwise INPUT
@@ -620,30 +620,6 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int group = (warp - 2) >> 2, gw = (warp - 2) & 3;
       const int c2 = lane & 15, pos = gw * 2 + (lane >> 4);
       const int x0 = (pos % PXN) * TX, r0 = (pos / PXN) * TY;
-      // The group's leader thread issues the TMA of the group's NEXT input box (chunk + 2, same stage) as soon as all
-      // four warps have read the current one -- not when the MMAs release the stage: the box is ~1/3 of a stage and its
-      // load latency (~2 us under load) was fully exposed with two stages.
-      auto issue_box = [&](int t2, int c2, bool l2_only) {
-        while (c2 >= p.num_chunks) {
-          c2 -= p.num_chunks;
-          t2 += gridDim.x;
-        }
-        if (t2 >= num_tiles) return;
-        constexpr int th = 128 / MW, tpf = MW / th;
-        const int mt2 = t2 / p.num_n_tiles, st = group;  // S == 2: stage = chunk & 1 = group
-        if (l2_only) {
-          // the shared-memory box is still being read: start the HBM -> L2 leg of the next box now, so that the TMA load
-          // issued after the depthwise pass finds its lines in L2 (the group's box round trip is exposed, S == 2)
-          if (!PW_ABL(32)) tma_prefetch_4d(&tmA, c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
-          return;
-        }
-        mbar_arrive_expect_tx(&full[st], (PW_ABL(16) ? 0 : p.box_bytes) + DWK * DWK * 128 + (p.dw_bias ? 128 : 0));
-        if (!PW_ABL(16)) tma_load_4d(dw_box(st), &tmA, &full[st], c2 * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
-        tma_load_2d(dw_wts(st), &tmDW, &full[st], c2 * 32, 0);
-        if (p.dw_bias) tma_load_2d(dw_bia(st), &tmDB, &full[st], c2 * 32, 0);
-      };
-      const bool leader = gw == 0 && lane == 0;
-      if (leader) issue_box(blockIdx.x, group, false);  // the group's first chunk
       int chunk = 0;
       PWT(td0);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -653,7 +629,6 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_wait(&full[stage], phase);
             PWT(td2);
             PWT_ACC(6, td1, td2);
-            if (leader) issue_box(t, c + 2, true);
             typedef unsigned long long U2;  // two packed fp32 channels
             const U2* in2 = reinterpret_cast<const U2*>(dw_box(stage));
             const U2* w2 = reinterpret_cast<const U2*>(dw_wts(stage));
@@ -691,11 +666,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             __syncwarp();
             PWT(td3);
             PWT_ACC(7, td2, td3);
-            if (lane == 0) mbar_arrive(&box_empty[stage]);  // this warp has read the box
-            if (leader) {
-              mbar_wait(&box_empty[stage], phase);
-              issue_box(t, c + 2, false);
-            }
+            if (lane == 0) mbar_arrive(&box_empty[stage]);  // this warp has read the box (warp 18 refills it)
             PWT(td4);
             PWT_ACC(8, td3, td4);
             mbar_wait(&empty[stage], phase ^ 1);  // the MMAs of this stage's previous chunk have read its A tiles
@@ -775,6 +746,49 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     PWT(ts5);
     PWT_ACC(11, ts0, ts5);
     if (warp == 2) { PWT_FLUSH(6, 12); }
+    }
+  } else if (warp == 18) {
+    // ---- depthwise-box producer (DWK > 0): group g = chunk & 1 owns box g; chunk i + 2 is loaded into it as soon as the four
+    // warps of the group have READ chunk i -- not when the MMAs release the stage (the box is ~1/3 of a stage and its load
+    // latency was fully exposed with two stages), and by this warp rather than by one of the depthwise warps: the warp
+    // that waited for its three siblings wrote its share of the A tile last and delayed every chunk by that wait.
+    if constexpr (DWK > 0) {
+      if (lane == 0) {
+        constexpr int th = 128 / MW, tpf = MW / th;
+        struct It {
+          int t, c;
+        };
+        auto advance = [&](It& it) {
+          if (++it.c == p.num_chunks) {
+            it.c = 0;
+            it.t += gridDim.x;
+          }
+        };
+        auto load_box = [&](const It& it, int st) {
+          const int mt2 = it.t / p.num_n_tiles;
+          mbar_arrive_expect_tx(&full[st], (PW_ABL(16) ? 0 : p.box_bytes) + DWK * DWK * 128 + (p.dw_bias ? 128 : 0));
+          if (!PW_ABL(16))
+            tma_load_4d(dw_box(st), &tmA, &full[st], it.c * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
+          tma_load_2d(dw_wts(st), &tmDW, &full[st], it.c * 32, 0);
+          if (p.dw_bias) tma_load_2d(dw_bia(st), &tmDB, &full[st], it.c * 32, 0);
+        };
+        auto prefetch_box = [&](const It& it) {  // HBM -> L2 leg of a later box, no shared memory needed
+          const int mt2 = it.t / p.num_n_tiles;
+          if (!PW_ABL(32)) tma_prefetch_4d(&tmA, it.c * 32, -(DWK / 2), (mt2 % tpf) * th - DWK / 2, mt2 / tpf);
+        };
+        It nx = {(int)blockIdx.x, 0};  // next chunk to load
+        for (int j = 0; j < 2 && nx.t < num_tiles; ++j, advance(nx)) load_box(nx, j);
+        It pf = nx;                    // next chunk to prefetch into L2 (two chunks ahead of the loads)
+        for (int j = 0; j < 2 && pf.t < num_tiles; ++j, advance(pf)) prefetch_box(pf);
+        for (int i = 0; nx.t < num_tiles; ++i, advance(nx)) {
+          mbar_wait(&box_empty[i & 1], (uint32_t)((i >> 1) & 1));  // chunk i has been read by its group
+          load_box(nx, i & 1);                                       // chunk i + 2
+          if (pf.t < num_tiles) {
+            prefetch_box(pf);                                        // chunk i + 4
+            advance(pf);
+          }
+        }
+      }
     }
   } else {
     // 8 epilogue warps: two per TMEM lane quadrant, taking alternate 16-column groups.
