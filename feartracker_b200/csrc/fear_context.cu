@@ -70,6 +70,7 @@ struct Options {
                       // depthwise + 1x1 as one tcgen05 kernel (pw_tc_kernel<DWK, MW>): bit-identical to the unfused pair,
                       // the depthwise maps are never written.  Round 2: 3.56 -> 3.40 ms / step, -2.3 GB DRAM traffic / step.
                       // 8 = the expand-1 blocks (xif2_2, xif2_3: dw 3x3 -> 1x1 24 -> 24 -> + x) as one CUDA-core kernel
+  int pw_ts = 1;      // 1: plain 1x1 GEMMs take their A operand from tensor memory (pw_tc_kernel<0, 16, true>); 0: from shared memory
   int fuse_stem = 1;  // 1: stem + xif1_0 in one kernel (stem_xif1_fused_kernel) when the map tiles by 16x32
   int fuse_irf = 1;   // 1: xif2_0 (expand -> depthwise s2 -> project) as ONE tcgen05 kernel (irf_s2_fused_kernel)
   int dw = 3;  // 3 = auto (default); 0 = one pixel per thread, 1 = register-strip kernel, 2 = rolling-window kernel,
@@ -223,7 +224,7 @@ static int launch_pw(FearContext* c, int stage, cudaStream_t s, const float* A, 
   }
   if (pw_impl == IMPL_TC && tc::pw_supported(w.cin, w.cout)) {
     LaunchScope scope(c, stage, s);
-    int r = tc::launch_pw(s, A, lda, w.w_hi, w.w_lo, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu);
+    int r = tc::launch_pw(s, A, lda, w.w_hi, w.w_lo, w.b, R, ldr, C, ldc, M, w.cout, w.cin, relu, c->opt.pw_ts != 0);
     if (r) return set_err(r, "tcgen05 pw launch failed (%d)", r);
     return check_launch("tc::pw");
   }
@@ -1128,6 +1129,10 @@ extern "C" int fear_set_option(FearContext* c, const char* key, const char* valu
   }
   if (!strcmp(key, "fuse_dwpw")) {
     o.fuse_dwpw = atoi(value) & 15;  // bit 0: 16x16-stage backbone blocks, bit 1: the head's SepConvs, bit 2: also the 32x32-stage blocks, bit 3: expand-1 blocks
+    return 0;
+  }
+  if (!strcmp(key, "pw_ts")) {
+    o.pw_ts = atoi(value) != 0;
     return 0;
   }
   if (!strcmp(key, "fuse_stem")) {

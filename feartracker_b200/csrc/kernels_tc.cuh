@@ -396,6 +396,7 @@ struct PwParams {
                   // N tile and one K chunk) and the ring stages hold activations only
 };
 
+constexpr int kPwTsSlotCol = 384;  // TS form: two 64-column (32 hi + 32 lo) A slots behind <= 384 accumulator columns
 constexpr int kPwThreads = 608;  // producer, MMA, 8 split / depthwise warps, 8 epilogue warps, depthwise-box producer
 
 // DWK = 0: plain 1x1 conv.  DWK = 3 | 5 (EXPERIMENTAL, opt-in "fuse_dwpw"; 16x16 maps, stride 1): the layer's input is
@@ -404,7 +405,14 @@ constexpr int kPwThreads = 608;  // producer, MMA, 8 split / depthwise warps, 8 
 // groups of four "split" warps take alternate chunks, run the depthwise conv out of shared memory (same FMA order as
 // dw_tma_kernel => same fp32 values as the unfused pair of kernels) and write the (hi, lo) A tiles directly in the
 // SWIZZLE_128B K-major layout the MMA descriptors expect.  Everything downstream is unchanged.
-template <int DWK, int MW = 16>
+//
+// TS = true (plain 1x1 convs whose accumulators leave 128 TMEM columns free): the A operand goes to TENSOR MEMORY.  The eight
+// operand-split warps read the raw tile once (row per lane, swizzle-aware LDS.128), split it in registers and store
+// (hi, lo) with tcgen05.st into one of two 64-column slots; the MMAs take A from TMEM.  No lo tile is written to and no A
+// tile is read back from shared memory -- pw_tc_kernel is bound by the shared-memory port (tools/pw_timing.py) --, the two
+// 16 KB lo buffers become ring stages, and the N = 2 NT stacked MMA runs at the TS rate.  Same products in the same order as
+// the shared-memory form: bit-identical results.
+template <int DWK, int MW = 16, bool TS = false>
 __global__ void __launch_bounds__(kPwThreads, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
              const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmC,
@@ -416,7 +424,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // then pure landing space (raw A tile + weight tiles), i.e. every byte of it can be "in flight" -- these GEMMs are
   // bound by bytes in flight / loaded latency (Little's law: 3 x 44 KB per SM gave 22 B/clk), not by the tensor pipe.
   uint8_t* lo_buf = smem + p.w_region;
-  uint8_t* ring = lo_buf + (DWK == 0 ? 2 * kCorrABytes : 0);
+  static_assert(!TS || DWK == 0, "the tensor-memory A operand is for the plain 1x1 convs");
+  uint8_t* ring = lo_buf + ((DWK == 0 && !TS) ? 2 * kCorrABytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + S * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* split = bars + S;  // DWK == 0: split[0..1] = lo buffer written; DWK > 0: per stage
@@ -458,7 +467,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&split[s], DWK ? 4 : 8);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], TS ? 9 : 1);  // TS: the 8 split warps read the A tile, the MMAs only the weight tiles
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -574,6 +583,18 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (PW_ABL(1)) break;
             const uint64_t dah = umma_desc_k_sw128(ah + j * 32), dal = umma_desc_k_sw128(al + j * 32);
             const uint64_t dbh = umma_desc_k_sw128(bh + j * 32), dbl = umma_desc_k_sw128(bl + j * 32);
+            if constexpr (TS) {
+              const uint32_t tah = tmem_base + kPwTsSlotCol + (q & 1) * 64 + j * 8, tal = tah + 32;
+              if (p.split_acc) {
+                mma_tf32_ts(d, tah, dbh, idesc2, (c | j) != 0);
+                mma_tf32_ts(d + p.NT, tal, dbh, idesc, 1);
+              } else {
+                mma_tf32_ts(d, tah, dbh, idesc, (c | j) != 0);
+                mma_tf32_ts(d, tal, dbh, idesc, 1);
+                mma_tf32_ts(d, tah, dbl, idesc, 1);
+              }
+              continue;
+            }
             // short K (<= 2 chunks): a handful of accumulations, the truncating adder is harmless and a single
             // accumulator halves the TMEM read (64 B/clk/SM) that dominates the epilogue of the wide layers
             if (p.split_acc) {
@@ -710,15 +731,51 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else {
     int q = 0;
     PWT(ts0);
+    const int qd = warp & 3, hh = (warp - 2) >> 2, row = qd * 32 + lane;  // (TS) TMEM lane quadrant, channel half, tile row
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       for (int c = 0; c < p.num_chunks; ++c, ++q) {
         PWT(ts1);
         mbar_wait(&full[stage], phase);
         PWT(ts2);
         PWT_ACC(6, ts1, ts2);
-        mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer
+        mbar_wait(&lo_empty[q & 1], (uint32_t)(((q >> 1) & 1) ^ 1));  // the MMAs of chunk q - 2 have read this lo buffer / slot
         PWT(ts3);
         PWT_ACC(9, ts2, ts3);
+        if constexpr (TS) {
+          tc_fence_after();
+          if (!PW_ABL(2)) {
+            const float4* xrow = reinterpret_cast<const float4*>(a_hi(stage) + row * 128);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 v = xrow[(hh * 4 + j) ^ (row & 7)];  // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+              const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;  // what kind::tf32 reads from the raw word
+                hi[4 * j + e] = h;
+                lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+              }
+            }
+            const uint32_t tdst = tmem_base + kPwTsSlotCol + (q & 1) * 64 + ((uint32_t)(qd * 32) << 16);
+            tmem_st_32x16(tdst + hh * 16, hi);
+            tmem_st_32x16(tdst + 32 + hh * 16, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&empty[stage]);  // this warp has read the stage's A tile
+            mbar_arrive(&split[q & 1]);
+          }
+          PWT(ts4t);
+          PWT_ACC(10, ts3, ts4t);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         float4* ah = reinterpret_cast<float4*>(a_hi(stage));
         float4* al = reinterpret_cast<float4*>(lo_buf + (q & 1) * kCorrABytes);
 #pragma unroll
@@ -992,6 +1049,7 @@ inline bool pw_supported(int cin, int cout) {
 
 inline int init_pw() {
   if (cudaFuncSetAttribute(pw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(pw_tc_kernel<0, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(pw_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(pw_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
       cudaFuncSetAttribute(pw_tc_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwMaxSmem) != cudaSuccess ||
@@ -1003,8 +1061,18 @@ inline int init_pw() {
 }
 
 // w_hi / w_lo: tf32-split copies of the [N][K] weights (device).
+// Tile width for the tensor-memory (TS) form: the accumulators may use 384 TMEM columns (2 sets x (main + correction) x NT or
+// 2 sets x NT), i.e. NT <= 96 with split accumulators and <= 192 without; the layer is cut into the fewest such tiles, the last
+// one may hang over N (weight rows >= N are zero-filled by TMA, the store is clipped).
+inline int pw_tile_n_ts(int N, bool split_acc) {
+  const int limit = split_acc ? 96 : 192;
+  const int Np = (N + 15) & ~15;
+  const int tiles = (Np + limit - 1) / limit;
+  return (((Np + tiles - 1) / tiles) + 15) & ~15;
+}
+
 inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi, const float* w_lo, const float* bias,
-                     const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu) {
+                     const float* R, int ldr, float* C, int ldc, int M, int N, int K, int relu, bool ts_form = true) {
   if (!available()) return -20;
   PwParams p;
   p.bias = bias;
@@ -1015,24 +1083,32 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   p.M = M;
   p.N = N;
   p.num_chunks = (K + 31) / 32;
-  p.NT = pw_tile_n(N, p.num_chunks == 1);
+  p.split_acc = p.num_chunks > 2;
+  if (ts_form) {
+    // only where the narrower TS tiles cut the layer without waste (N = 256 / 336 with split accumulators would pad to 288 /
+    // 384 columns: measured slower than the shared-memory form with NT = 128 / 112)
+    const int nt = pw_tile_n_ts(N, p.split_acc);
+    if (((N + 15) & ~15) % nt) ts_form = false;
+  }
+  p.NT = ts_form ? pw_tile_n_ts(N, p.split_acc) : pw_tile_n(N, p.num_chunks == 1);
   if (!p.NT) return -21;
   p.num_n_tiles = (((N + 15) & ~15) + p.NT - 1) / p.NT;
   p.last_ksteps = ((K - 32 * (p.num_chunks - 1)) + 7) / 8;
-  p.split_acc = p.num_chunks > 2;
   p.acc_stride = p.split_acc ? 2 * p.NT : p.NT;
   p.relu = relu;
   p.dw_relu = p.dw_bias = p.box_bytes = 0;
   p.map_w = 16;
   const bool resident = p.num_n_tiles == 1 && p.num_chunks == 1;
   p.w_region = resident ? 2 * p.NT * 128 : 0;
-  p.stage_bytes = resident ? kCorrABytes : kCorrABytes + 2 * p.NT * 128;  // landing space only (lo tiles: 2 extra buffers)
-  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region - 2 * kCorrABytes) / p.stage_bytes;
+  p.stage_bytes = resident ? kCorrABytes : kCorrABytes + 2 * p.NT * 128;  // landing space only
+  const int lo_bytes = ts_form ? 0 : 2 * kCorrABytes;                      // (shared-memory form: two lo tiles beside the ring)
+  p.stages = (kPwMaxSmem - 1024 - kPwTailBytes - p.w_region - lo_bytes) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return -22;
   int cols = 32;
   while (cols < 2 * p.acc_stride) cols <<= 1;
-  p.tmem_cols = cols;
+  p.tmem_cols = ts_form ? 512 : cols;
+  if (ts_form && 2 * p.acc_stride > kPwTsSlotCol) return -21;
   CUtensorMap tmA, tmWh, tmWl;
   int r = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 32);
   if (r) return r;
@@ -1045,14 +1121,16 @@ inline int launch_pw(cudaStream_t s, const float* A, int lda, const float* w_hi,
   CUtensorMap tmC;  // output: [M][N] window of C (pitch ldc); 32 x 16 boxes, SWIZZLE_64B staging; clips the tails
   r = make_tmap_2d(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 16);
   if (r) return r;
-  const int smem_bytes = p.w_region + 2 * kCorrABytes + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
+  const int smem_bytes = p.w_region + lo_bytes + p.stages * p.stage_bytes + 1024 + kPwTailBytes;
 #ifdef FEAR_PW_TIMING
   p.timing_id = pw_timing_next()++;
   pw_timing_info()[p.timing_id & 63] = {M, N, K, 0, 0, grid, tiles, p.num_chunks};
 #endif
-  if (launch_pdl(pw_tc_kernel<0>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA, tmA, p) !=
-      cudaSuccess)
-    return -23;
+  const cudaError_t e =
+      ts_form ? launch_pdl(pw_tc_kernel<0, 16, true>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA,
+                           tmA, p)
+              : launch_pdl(pw_tc_kernel<0>, dim3(grid), dim3(kPwThreads), (size_t)smem_bytes, s, tmA, tmWh, tmWl, tmC, tmA, tmA, p);
+  if (e != cudaSuccess) return -23;
   return 0;
 }
 

@@ -163,6 +163,8 @@ int fear_corr_nhwc_f32(const float* d_zt, int Bz, float* d_cat, int B, void* str
  *                    their depthwise conv inside the 1x1 GEMM kernel, 8 = the expand-1 blocks (depthwise 3x3 -> 1x1 24 -> 24
  *                    -> + x) run as one CUDA-core kernel; all bit-identical to the two-kernel paths (the depthwise maps are
  *                    never written)
+ *   "pw_ts"        : "1" (default) plain 1x1 GEMMs take the activation operand from tensor memory (TS-form MMA) where their
+ *                    accumulators leave room for it | "0" both operands in shared memory; bit-identical
  *   "pdl"          : "1" (default) programmatic dependent launch (process-wide) */
 int fear_set_option(FearContext* h, const char* key, const char* value);
 /* Number of kernels launched by this handle since creation (for bench's gpu_launches). */

@@ -281,6 +281,22 @@ def test_fused_depthwise_pointwise_is_bit_identical(net, mask):
     assert torch.equal(ref[R], got[R]) and torch.equal(ref[C], got[C])
 
 
+def test_tensor_memory_operand_gemm_is_bit_identical(net):
+    """pw_ts: the plain 1x1 GEMMs with the activation operand in tensor memory (TS-form tcgen05.mma, narrower N tiles) issue
+    the same products in the same order as the shared-memory form."""
+    zt, xt, _, _ = fo.synthetic_crops(3)
+    zf = net.get_features(zt.cuda())
+    ref = net.track(xt.cuda(), zf)
+    net.set_option("pw_ts", "0")
+    try:
+        zf0 = net.get_features(zt.cuda())
+        got = net.track(xt.cuda(), zf0)
+    finally:
+        net.set_option("pw_ts", "1")
+    assert torch.equal(zf, zf0)
+    assert torch.equal(ref[R], got[R]) and torch.equal(ref[C], got[C])
+
+
 def test_uint8_input_path_is_bit_identical(net):
     """Raw uint8 HWC crops normalised inside the stem kernel == float crops normalised on the host."""
     _, _, zu, xu = fo.synthetic_crops(3)
