@@ -24,7 +24,27 @@ constexpr int kFsSH = kFsTH + 2, kFsSW = kFsTW + 2;    // stem tile incl. the de
 constexpr int kFsPH = 2 * kFsSH + 1;                   // input patch rows: 37
 constexpr int kFsPW = 2 * kFsSW + 1;                   // input patch cols: 69
 constexpr int kFsPP = 72;                              // patch row pitch (floats; 16-byte aligned rows)
-constexpr int kFsPitch = 20;                           // floats per stem pixel in smem (16 + 4: conflict-free LDS.128)
+constexpr int kFsPitch = 20;                           // floats per stem pixel in smem (16 + 4 pad)
+// Stem tile addressing.  A thread owns two horizontally adjacent pixels, so the lanes of a quarter warp touch pixels q, q + 2,
+// ... q + 14: with a 5-quad pixel pitch the 16-byte chunk c of those pixels falls on bank quads (2 j + c) mod 8 -- lanes j and
+// j + 4 collide (ncu: 2 wavefronts per ideal wavefront on every STS.128 / LDS.128 of the tile, L1/TEX 74 % busy).  Storing
+// chunk c of pixel q at slot c ^ ((q >> 3) & 1) separates them: conflict free for writes and reads.  Even chunks sit at
+// base + 16 s + 16 c, odd chunks at base - 16 s + 16 c (s = the swizzle bit), i.e. two base pointers per pixel.
+struct FsPix {
+  const float* e;  // base for chunks 0, 2
+  const float* o;  // base for chunks 1, 3
+};
+__device__ __forceinline__ FsPix fs_pix(const float* stem, int q) {
+  const int s4 = ((q >> 3) & 1) << 2;  // swizzle offset in floats
+  const float* b = stem + q * kFsPitch;
+  return {b + s4, b - s4};
+}
+__device__ __forceinline__ float4 fs_ld(const FsPix& p, int c4) {
+  return *reinterpret_cast<const float4*>(((c4 & 1) ? p.o : p.e) + 4 * c4);
+}
+__device__ __forceinline__ void fs_st(const FsPix& p, int c4, float4 v) {
+  *reinterpret_cast<float4*>(const_cast<float*>(((c4 & 1) ? p.o : p.e) + 4 * c4)) = v;
+}
 constexpr int kFsThreads = 320;
 // All weights of the fused kernel (3.4 KB), passed BY VALUE as a __grid_constant__ kernel parameter: they live in
 // the constant bank, every index below is a compile-time constant after unrolling, so each FFMA takes its weight
@@ -129,16 +149,17 @@ stem_xif1_fused_kernel(const __grid_constant__ CUtensorMap tmImg, float* __restr
     const int gx = ox0 - 1 + 2 * j;
     const bool in_y = gy >= 0 && gy < Hs;
     const bool in0 = in_y && gx >= 0 && gx < Ws, in1 = in_y && gx + 1 >= 0 && gx + 1 < Ws;
-    float4* d0 = reinterpret_cast<float4*>(stem + (sy * kFsSW + 2 * j) * kFsPitch);
-    float4* d1 = reinterpret_cast<float4*>(stem + (sy * kFsSW + 2 * j + 1) * kFsPitch);
+    const FsPix d0 = fs_pix(stem, sy * kFsSW + 2 * j), d1 = fs_pix(stem, sy * kFsSW + 2 * j + 1);
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-      d0[c4] = in0 ? make_float4(fmaxf(a0[4 * c4], 0.f), fmaxf(a0[4 * c4 + 1], 0.f), fmaxf(a0[4 * c4 + 2], 0.f),
-                                 fmaxf(a0[4 * c4 + 3], 0.f))
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
-      d1[c4] = in1 ? make_float4(fmaxf(a1[4 * c4], 0.f), fmaxf(a1[4 * c4 + 1], 0.f), fmaxf(a1[4 * c4 + 2], 0.f),
-                                 fmaxf(a1[4 * c4 + 3], 0.f))
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      fs_st(d0, c4,
+            in0 ? make_float4(fmaxf(a0[4 * c4], 0.f), fmaxf(a0[4 * c4 + 1], 0.f), fmaxf(a0[4 * c4 + 2], 0.f),
+                              fmaxf(a0[4 * c4 + 3], 0.f))
+                : make_float4(0.f, 0.f, 0.f, 0.f));
+      fs_st(d1, c4,
+            in1 ? make_float4(fmaxf(a1[4 * c4], 0.f), fmaxf(a1[4 * c4 + 1], 0.f), fmaxf(a1[4 * c4 + 2], 0.f),
+                              fmaxf(a1[4 * c4 + 3], 0.f))
+                : make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
   __syncthreads();
@@ -153,10 +174,11 @@ stem_xif1_fused_kernel(const __grid_constant__ CUtensorMap tmImg, float* __restr
     for (int ky = 0; ky < 3; ++ky) {
       float4 x[4][4];  // 4 stem columns x 16 channels of this row
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const FsPix px = fs_pix(stem, (oy + ky) * kFsSW + 2 * j + i);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          x[i][c4] = *reinterpret_cast<const float4*>(stem + ((oy + ky) * kFsSW + 2 * j + i) * kFsPitch + 4 * c4);
+        for (int c4 = 0; c4 < 4; ++c4) x[i][c4] = fs_ld(px, c4);
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -190,12 +212,11 @@ stem_xif1_fused_kernel(const __grid_constant__ CUtensorMap tmImg, float* __restr
         p1[o] = fmaf(d1[k], wv, p1[o]);
       }
     }
-    const float4* r0 = reinterpret_cast<const float4*>(stem + ((oy + 1) * kFsSW + 2 * j + 1) * kFsPitch);
-    const float4* r1 = reinterpret_cast<const float4*>(stem + ((oy + 1) * kFsSW + 2 * j + 2) * kFsPitch);
+    const FsPix r0 = fs_pix(stem, (oy + 1) * kFsSW + 2 * j + 1), r1 = fs_pix(stem, (oy + 1) * kFsSW + 2 * j + 2);
     float4* o0 = reinterpret_cast<float4*>(out + (((long long)b * Hs + oy0 + oy) * Ws + ox0 + 2 * j) * 16);
 #pragma unroll
     for (int o4 = 0; o4 < 4; ++o4) {
-      const float4 q0 = r0[o4], q1 = r1[o4];
+      const float4 q0 = fs_ld(r0, o4), q1 = fs_ld(r1, o4);
       o0[o4] = make_float4(p0[4 * o4] + q0.x, p0[4 * o4 + 1] + q0.y, p0[4 * o4 + 2] + q0.z, p0[4 * o4 + 3] + q0.w);
       o0[4 + o4] = make_float4(p1[4 * o4] + q1.x, p1[4 * o4 + 1] + q1.y, p1[4 * o4 + 2] + q1.z, p1[4 * o4 + 3] + q1.w);
     }
