@@ -485,7 +485,28 @@ def main():
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
             "algorithmic_bytes_per_launch": int(bytes_per_launch),
+            "how": "CUDA events around every correlation launch inside K extra steps (includes the launch latency the event "
+                   "pair exposes); back_to_back = the same launch shape issued 40 times in a row on rotating > L2 buffers",
         }
+        if rank == 0:
+            # the same kernel and launch shape (2 B frames) in a tight loop: what the kernel sustains once launch latency and
+            # the prologue are hidden behind the previous launch, as they are inside the step with programmatic dependent launch
+            frames = 2 * B
+            zt_b = torch.randn(frames, 64, 256, device=dev)
+            cats = [torch.randn(frames, 256, 320, device=dev) for _ in range(2)]
+            lib_c, st = _lib.load(), torch.cuda.current_stream(dev).cuda_stream
+            for c_ in cats:
+                _lib.check(lib_c.fear_corr_nhwc_f32(zt_b.data_ptr(), frames, c_.data_ptr(), frames, st), "fear_corr_nhwc_f32")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i_ in range(40):
+                _lib.check(lib_c.fear_corr_nhwc_f32(zt_b.data_ptr(), frames, cats[i_ & 1].data_ptr(), frames, st), "fear_corr_nhwc_f32")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us_b2b = e0.elapsed_time(e1) * 1e3 / 40
+            gbs = CORR_BYTES_PER_FRAME // 2 * frames / (us_b2b * 1e-6) / 1e9
+            roofline["back_to_back"] = {"us_per_launch": us_b2b, "achieved": gbs, "frac": gbs / peak}
+            del zt_b, cats
     step_ms_sum = sum(v[0] for v in stages.values()) / args.steps
     path_gbs = PATH_BYTES_PER_FRAME * B / (ms_total / args.steps * 1e-3) / 1e9
     stage_report = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
